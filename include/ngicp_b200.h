@@ -1,0 +1,167 @@
+/* ngicp_b200.h — C ABI of the B200-native nano_gicp scan-to-map hot path.
+ *
+ * This is the drop-in boundary: the reference has no FFI for this path, its boundary is the C++
+ * class nano_gicp::NanoGICP<PointSource,PointTarget> (reference src/dlio/include/nano_gicp/nano_gicp.h:63-150)
+ * statically linked into DLIO's odom node. include/nano_gicp/nano_gicp.h in this repo keeps that
+ * class surface and forwards every call to the entry points below; INTEGRATION.md shows the wiring.
+ * Each entry point names the reference member it replaces (paths relative to reference src/dlio/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; every function returns an int status
+ *    (NGICP_OK = 0). No exceptions, no abort(), nothing printed. ngicp_last_error() gives text.
+ *  - host point clouds: any float AoS with xyz at floats 0..2 of every record, `stride_bytes` apart
+ *    (the reference's dlio::Point is 32 bytes: include/dlio/dlio.h:85-108).
+ *  - 4x4 matrices are COLUMN-MAJOR (Eigen's default storage): element (r,c) at [4*c+r].
+ *    6x6 H is symmetric, written in full.
+ *  - host covariance lists are the reference's CovarianceList layout: n x Matrix4d, 16 doubles each,
+ *    column-major, only the upper-left 3x3 block non-zero (nano_gicp.h:59).
+ *  - one CUDA stream per handle; handles are independent and may be driven from different host
+ *    threads concurrently (DLIO does: gicp on the lidar thread, gicp_temp on the submap thread,
+ *    src/dlio/odom.cc:798-801,1005,1737). A single handle is not thread-safe (neither is the reference).
+ *  - indices ("trees") are reference-counted so one handle can build a submap index and another
+ *    adopt it (odom.cc:1737-1738 -> :995).
+ *  - every compute entry point runs hand-written sm_100a CUDA kernels; there is no CPU fallback.
+ */
+#ifndef NGICP_B200_H_
+#define NGICP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngicp_handle ngicp_handle; /* one NanoGICP object                          */
+typedef struct ngicp_index ngicp_index;   /* one nanoflann::KdTreeFLANN<PointT> (cloud+index) */
+
+enum {
+  NGICP_OK = 0,
+  NGICP_ERR_INVALID = 1,   /* bad argument / missing cloud, index or covariances        */
+  NGICP_ERR_CUDA = 2,      /* CUDA runtime error (text in ngicp_last_error)              */
+  NGICP_ERR_NO_DEVICE = 3, /* no usable sm_100 device: the library never falls back to CPU */
+  NGICP_ERR_UNSUPPORTED = 4,
+  NGICP_ERR_LM_NOT_CONVERGED = 5 /* LM inner loop exhausted ("lm not converged!!", lsq_registration.cc:124-127);
+                                    outputs are still written, converged = 0              */
+};
+
+/* nano_gicp.h:61 — same order as the reference enum */
+enum { NGICP_REG_NONE = 0, NGICP_REG_MIN_EIG = 1, NGICP_REG_NORMALIZED_MIN_EIG = 2, NGICP_REG_PLANE = 3, NGICP_REG_FROBENIUS = 4 };
+
+enum { NGICP_SOURCE = 0, NGICP_TARGET = 1 };
+
+/* Configuration = the reference's setters. Defaults (ngicp_default_params) are the reference's
+ * constructor defaults: nano_gicp.cc:53-66, lsq_registration.cc:53-67. */
+typedef struct ngicp_params {
+  int k_correspondences;        /* setCorrespondenceRandomness   nano_gicp.cc:82-84   (default 20)      */
+  double max_corr_dist;         /* setMaxCorrespondenceDistance  nano_gicp.cc:87-89   (default FLT_MAX) */
+  int regularization;           /* setRegularizationMethod       nano_gicp.cc:92-94   (default PLANE)   */
+  int max_iterations;           /* setMaximumIterations          lsq_registration.cc:83-85  (64)        */
+  double rotation_epsilon;      /* setRotationEpsilon            lsq_registration.cc:73-75  (2e-3)      */
+  double transformation_epsilon;/* setTransformationEpsilon      lsq_registration.cc:78-80  (5e-4)      */
+  double lm_init_lambda_factor; /* setInitialLambdaFactor        lsq_registration.cc:88-90  (1e-9)      */
+  int lm_max_iterations;        /* lm_max_iterations_            lsq_registration.cc:62     (10)        */
+  int use_gauss_newton;         /* lsq_optimizer_type_           lsq_registration.cc:60     (0 = LM)    */
+} ngicp_params;
+
+void ngicp_default_params(ngicp_params* p);
+const char* ngicp_version(void);
+/* text of the last error on this handle (or, with h == NULL, of the calling thread) */
+const char* ngicp_last_error(const ngicp_handle* h);
+
+/* NanoGICP::NanoGICP / ~NanoGICP (nano_gicp.cc:53-69). device = CUDA ordinal. */
+int ngicp_create(int device, ngicp_handle** out);
+int ngicp_destroy(ngicp_handle* h);
+int ngicp_set_params(ngicp_handle* h, const ngicp_params* p);
+int ngicp_get_params(const ngicp_handle* h, ngicp_params* p);
+/* the handle's cudaStream_t (as void*), for callers that want to order their own work after it */
+void* ngicp_stream(ngicp_handle* h);
+int ngicp_synchronize(ngicp_handle* h);
+
+/* ---- index = nanoflann::KdTreeFLANN<PointT> (nanoflann_adaptor.h:57-152) ----------------------
+ * ngicp_index_build replaces KdTreeFLANN::setInputCloud -> KDTreeSingleIndexAdaptor::buildIndex
+ * (nanoflann_adaptor.h:132-138, nanoflann.h:1405-1417): uploads the cloud, computes voxel keys,
+ * Morton-sorts them with a radix sort and builds the multi-level voxel hash. The new index holds
+ * one reference owned by the caller. `h` supplies device, stream and scratch memory. */
+int ngicp_index_build(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes, ngicp_index** out);
+/* same, cloud already in device memory as packed float4 (x,y,z,unused) */
+int ngicp_index_build_device(ngicp_handle* h, const void* d_points_f4, size_t n, ngicp_index** out);
+int ngicp_index_retain(ngicp_index* idx);
+int ngicp_index_release(ngicp_index* idx);
+size_t ngicp_index_size(const ngicp_index* idx);
+/* KdTreeFLANN::nearestKSearch (nanoflann_adaptor.h:141-152), batched over nq queries. Exact k-NN,
+ * fp32 distance ((dx*dx)+(dy*dy))+(dz*dz); every row ordered by (distance, index) ascending — the
+ * documented tie-break of this build (the reference keeps KD-visit order on ties, nanoflann.h:207-240).
+ * out_idx / out_sqd: nq x k, original point indices; rows with fewer than k hits padded with -1 / +inf. */
+int ngicp_knn(ngicp_handle* h, const ngicp_index* idx, const void* queries, size_t nq, size_t stride_bytes,
+              int k, int32_t* out_idx, float* out_sqd);
+/* the 64-bit voxel key of every point in ORIGINAL order (spec in DESIGN.md §keys; bit-exact vs oracle) */
+int ngicp_index_keys(ngicp_handle* h, const ngicp_index* idx, uint64_t* out_keys, float origin_h0[4]);
+
+/* ---- cloud / tree / covariance bookkeeping (nano_gicp.cc:97-171) ------------------------------ */
+/* setInputSource / setInputTarget (nano_gicp.cc:135-161): build an index over the cloud, attach it,
+ * DROP existing covariances of that side. The pointer-identity early-out of the reference
+ * (:136,:151) lives in the C++ wrapper, which owns the shared_ptr. */
+int ngicp_set_input(ngicp_handle* h, int which, const void* points, size_t n, size_t stride_bytes);
+/* attach an existing index (the `target_kdtree_ = submap_kdtree` assignment, odom.cc:995, and
+ * registerInputSource/Target, nano_gicp.cc:119-132). Keeps covariances. Takes its own reference. */
+int ngicp_attach_index(ngicp_handle* h, int which, ngicp_index* idx);
+/* borrow the attached index (no reference taken) — `gicp_temp.target_kdtree_` read at odom.cc:1738 */
+ngicp_index* ngicp_get_index(ngicp_handle* h, int which);
+int ngicp_swap_source_and_target(ngicp_handle* h); /* nano_gicp.cc:97-104 */
+int ngicp_clear(ngicp_handle* h, int which);       /* clearSource / clearTarget, nano_gicp.cc:107-116 */
+
+/* calculateSourceCovariances / calculateTargetCovariances (nano_gicp.cc:174-191,330-392):
+ * k-NN (k = k_correspondences) + 3x3 covariance (/k) + regularisation; *density = source_density_. */
+int ngicp_compute_covariances(ngicp_handle* h, int which, float* density);
+/* getSourceCovariances / getTargetCovariances (nano_gicp.h:106-112): n x 16 doubles, original order */
+int ngicp_get_covariances(ngicp_handle* h, int which, double* out_4x4, size_t n);
+/* setSourceCovariances / setTargetCovariances (nano_gicp.cc:164-171) */
+int ngicp_set_covariances(ngicp_handle* h, int which, const double* in_4x4, size_t n);
+int ngicp_has_covariances(const ngicp_handle* h, int which, size_t* n);
+
+/* ---- registration (nano_gicp.cc:194-326, lsq_registration.cc:108-229) -------------------------- */
+/* update_correspondences (nano_gicp.cc:206-245). Optional outputs, original source order:
+ * corr[n_src] (target index or -1), sqd[n_src] (valid where corr >= 0), mahal n_src x 16 doubles. */
+int ngicp_update_correspondences(ngicp_handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* num_correspondences);
+/* linearize (nano_gicp.cc:248-302): re-associates, then H (6x6), b (6), error. H/b may be NULL. */
+int ngicp_linearize(ngicp_handle* h, const double T[16], double H[36], double b[6], double* error, int* num_correspondences);
+/* compute_error (nano_gicp.cc:305-326): cached correspondences / Mahalanobis of the last linearize */
+int ngicp_compute_error(ngicp_handle* h, const double T[16], double* error);
+/* pcl::Registration::align -> NanoGICP::computeTransformation -> LsqRegistration::computeTransformation
+ * (nano_gicp.cc:194-203, lsq_registration.cc:108-134). guess may be NULL (= identity, what DLIO passes,
+ * odom.cc:1005). Outputs: final_transformation_ (float 4x4), nr_iterations_, converged_,
+ * getFinalHessian(), getFinalError(). The 6x6 LM solve runs on the host. */
+int ngicp_align(ngicp_handle* h, const float guess[16], float T_out[16], int* nr_iterations, int* converged,
+                double H_final[36], double* final_error);
+/* pcl::transformPointCloud(*input_, output, final_transformation_) (lsq_registration.cc:133): fp32
+ * R*p+t of the source xyz into `out` (same stride; other fields untouched). DLIO discards it. */
+int ngicp_transform_source(ngicp_handle* h, const float T[16], void* out_points, size_t n, size_t stride_bytes);
+
+/* ---- batched / sharded work units (BASELINE configs 3 and 5; independent units, no collective) --
+ * Bulk covariance build over many keyframes in ONE pass: `points` holds all keyframes back to back,
+ * seg_offsets[n_seg+1] are the keyframe boundaries. Every keyframe gets its own index and its
+ * covariances come from neighbours inside that keyframe only (the reference computes covariances
+ * per scan and concatenates them per submap: nano_gicp.cc:174-181, odom.cc:1719-1729).
+ * out_4x4 (n x 16 doubles) and/or out_cov6 (n x 6 floats: xx,xy,xz,yy,yz,zz) may be NULL. */
+int ngicp_batch_covariances(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes,
+                            const int64_t* seg_offsets, int n_seg, double* out_4x4, float* out_cov6, float* seg_density);
+
+/* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
+typedef struct ngicp_timings {
+  float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */
+  float knn_ms;         /* K2: exact k-NN                                  */
+  float covariance_ms;  /* K3: covariance + regularisation                 */
+  float linearize_ms;   /* K4: sum over the align's linearize launches     */
+  float error_ms;       /* K5: sum over the align's compute_error launches */
+  int linearize_calls;
+  int error_calls;
+  int kernel_launches;  /* kernels launched by this handle since the last reset */
+} ngicp_timings;
+int ngicp_enable_timing(ngicp_handle* h, int on);
+int ngicp_get_timings(ngicp_handle* h, ngicp_timings* out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGICP_B200_H_ */

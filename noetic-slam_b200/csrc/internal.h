@@ -1,0 +1,148 @@
+// Host-side objects behind the C ABI (include/ngicp_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/ngicp_b200.h"
+#include "common.cuh"
+
+namespace ngicp {
+struct ReduceSlot;  // host-mapped result slot (linearize.cuh)
+
+// Covariances of one side (source / target), device-resident in the index's sorted order.
+struct CovSet {
+  float* cov6 = nullptr;     // [n][6] xx,xy,xz,yy,yz,zz
+  size_t n = 0;
+  bool valid = false;        // sorted copy present
+  std::vector<double> pending;  // [n][16] host-order Matrix4d list handed over before a matching index was attached
+  size_t pending_n = 0;
+  float density = 0.f;
+};
+}  // namespace ngicp
+
+// Device cloud + voxel index. Replaces nanoflann::KdTreeFLANN<PointT>
+// (reference src/dlio/include/nano_gicp/nanoflann_adaptor.h:57-152). Reference-counted because
+// DLIO hands the submap tree from one NanoGICP instance to another (odom.cc:1737-1738 -> :995).
+struct ngicp_index {
+  std::atomic<int> refs{1};
+  int device = 0;
+  int n = 0;
+  int n_seg = 1;
+  float4* pts = nullptr;                  // [n] Morton-sorted, .w = original index
+  unsigned long long* keys = nullptr;     // [n] sorted voxel keys
+  ngicp::CellSlot* table = nullptr;
+  uint32_t table_mask = 0;
+  ngicp::GridMeta* meta = nullptr;
+  float4* seg_origin = nullptr;           // [n_seg]
+  int* seg_start = nullptr;               // [n_seg+1]
+  std::vector<int64_t> seg_offsets_host;  // [n_seg+1]
+  ngicp::GridView view() const {
+    ngicp::GridView g;
+    g.pts = pts; g.table = table; g.meta = meta; g.seg_origin = seg_origin; g.seg_start = seg_start;
+    g.table_mask = table_mask; g.n = n; g.n_seg = n_seg;
+    return g;
+  }
+};
+
+struct ngicp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ngicp_params params;
+  ngicp_index* index[2] = {nullptr, nullptr};
+  ngicp::CovSet covs[2];
+  // registration scratch
+  int* corr = nullptr;          // [n_src] target sorted position or -1 (order: source sorted position)
+  size_t corr_cap = 0;
+  double lin_pose[12];          // pose of the last linearize (R row-major 9 + t 3), needed by compute_error
+  bool lin_valid = false;
+  double* partials = nullptr;   // [max_blocks][32] block partial sums
+  unsigned int* counter = nullptr;
+  ngicp::ReduceSlot* slot_host = nullptr;   // pinned + mapped
+  ngicp::ReduceSlot* slot_dev = nullptr;    // device alias of slot_host
+  unsigned long long seq = 0;
+  // host staging (pinned), grows on demand
+  void* stage_host = nullptr;
+  size_t stage_cap = 0;
+  cudaEvent_t stage_done = nullptr;  // last H2D out of stage_host
+  double* batch_partials = nullptr;  // batched reductions (allocated on first use)
+  size_t batch_partials_cap = 0;
+  // LM state (lsq_registration.h:151-168)
+  double lm_lambda = -1.0;
+  double final_hessian[36];
+  double final_error = 0.0;
+  int num_correspondences = 0;
+  // timing
+  bool timing = false;
+  ngicp_timings t;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::string err;
+};
+
+namespace ngicp {
+using Index = ::ngicp_index;
+using Handle = ::ngicp_handle;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_thread_error(const std::string& s);
+int fail(Handle* h, int code, const std::string& msg);
+#define NGICP_CUDA(h, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::ngicp::fail((h), NGICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- stage entry points (each in its own .cu) --------------------------------------------------
+// K1. xyz: device array of n points, `stride_floats` (3 or 4) floats apart.
+int build_index(Handle* h, const float* d_xyz, int stride_floats, int n, const int64_t* seg_offsets, int n_seg, Index** out);
+void free_index(Index* idx, cudaStream_t stream);
+// K2. self k-NN of every indexed point; nbr[n][k] = sorted positions (row = sorted position).
+// dens_term[n] (optional) = sum_{j>=1} d2_j / normalization, the per-point density term.
+int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term);
+// public k-NN: queries on device (float4), results in ORIGINAL indices, canonical order
+int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, int* d_out_idx, float* d_out_sqd);
+// K3. covariance + regularisation from the k-NN table
+int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6);
+// sum of n doubles -> *d_out (device), deterministic
+int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* d_out);
+// covariance layout conversions (host order <-> sorted order)
+int cov6_to_mat4_host_order(Handle* h, const Index* idx, const float* d_cov6, double* d_out16);
+int mat4_host_order_to_cov6(Handle* h, const Index* idx, const double* d_in16, float* d_cov6);
+int cov6_to_host_order(Handle* h, const Index* idx, const float* d_cov6, float* d_out6);
+int cov6_from_host_order(Handle* h, const Index* idx, const float* d_in6, float* d_cov6);
+// K4 / K5
+int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], double b[6], double* err, int* ncorr);
+int compute_error_device(Handle* h, const double T[16], double* err);
+int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr);
+int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out);
+
+// workspace helpers (stream-ordered pool)
+template <typename T>
+inline cudaError_t dev_alloc(T** p, size_t count, cudaStream_t s) {
+  return cudaMallocAsync(reinterpret_cast<void**>(p), count ? count * sizeof(T) : sizeof(T), s);
+}
+template <typename T>
+inline void dev_free(T* p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
+inline void count_launch(Handle* h, int k = 1) { h->t.kernel_launches += k; }
+
+struct StageTimer {
+  Handle* h; float* acc;
+  StageTimer(Handle* h_, float* acc_) : h(h_), acc(acc_) { if (h->timing) cudaEventRecord(h->ev[0], h->stream); }
+  ~StageTimer() {
+    if (!h->timing) return;
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    *acc += ms;
+  }
+};
+
+}  // namespace ngicp

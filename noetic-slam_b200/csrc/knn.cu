@@ -1,0 +1,151 @@
+// K2 — exact k-nearest-neighbour search over the Morton-sorted voxel hash.
+// Replaces nanoflann::KdTreeFLANN::nearestKSearch -> findNeighbors -> searchLevel
+// (reference src/dlio/include/nano_gicp/nanoflann_adaptor.h:141-152, nanoflann.h:1436-1460,
+// :1587-1666) and the k-NN call of calculate_covariances (src/nano_gicp/nano_gicp.cc:343).
+// One thread per query; queries run in Morton order so that a warp walks the same few cells.
+// Distances are the reference's fp32 metric bit for bit (common.cuh: sqdist_ref); result rows are
+// ordered by (distance, original index).
+#include "internal.h"
+
+namespace ngicp {
+
+namespace {
+
+template <class TK>
+__device__ __forceinline__ void self_query(const GridView& g, int j, int k, int start_count, int normalization,
+                                           int* __restrict__ nbr, double* __restrict__ dens_term, TK& best) {
+  const float4 q = __ldg(g.pts + j);
+  const int seg = find_segment(g.seg_start, g.n_seg, j);
+  grid_knn(g, q.x, q.y, q.z, seg, k, start_count, __int_as_float(0x7f800000), best);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int start_count, int normalization,
+                                                       int* __restrict__ nbr, double* __restrict__ dens_term) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n) return;
+  TopK<K> best;
+  self_query(g, j, k, start_count, normalization, nbr, dens_term, best);
+  int* row = nbr + (size_t)j * k;
+  if (k == K && (K % 4) == 0) {
+#pragma unroll
+    for (int i = 0; i < K; i += 4) reinterpret_cast<int4*>(row)[i / 4] = make_int4(best.p[i], best.p[i + 1], best.p[i + 2], best.p[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; i++) if (i < k) row[i] = best.p[i];
+  }
+  if (dens_term) {
+    // nano_gicp.cc:345-346: accumulate(k_sq_distances.begin()+1, end, 0.0) / normalization
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 1; i < K; i++) if (i < k) acc += (double)best.d[i];
+    dens_term[j] = acc / (double)normalization;
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(64) knn_self_dyn_kernel(GridView g, int k, int start_count, int normalization,
+                                                         int* __restrict__ nbr, double* __restrict__ dens_term) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n) return;
+  TopKDyn<KMAX> best;
+  best.cap = k;
+  self_query(g, j, k, start_count, normalization, nbr, dens_term, best);
+  int* row = nbr + (size_t)j * k;
+  for (int i = 0; i < k; i++) row[i] = best.p[i];
+  if (dens_term) {
+    double acc = 0.0;
+    for (int i = 1; i < k; i++) acc += (double)best.d[i];
+    dens_term[j] = acc / (double)normalization;
+  }
+}
+
+template <class TK>
+__device__ __forceinline__ void write_public(const GridView& g, const TK& best, int k, int cap, int* __restrict__ oi, float* __restrict__ od) {
+  for (int i = 0; i < k; i++) {
+    int p = -1; float d = __int_as_float(0x7f800000);
+    if (i < cap) { p = best.p[i]; d = best.d[i]; }
+    oi[i] = p >= 0 ? __float_as_int(__ldg(&g.pts[p].w)) : -1;
+    od[i] = p >= 0 ? d : __int_as_float(0x7f800000);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) knn_query_kernel(GridView g, const float4* __restrict__ q, int nq, int k, int start_count,
+                                                        int* __restrict__ out_idx, float* __restrict__ out_sqd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const float4 qq = __ldg(q + i);
+  TopK<K> best;
+  grid_knn(g, qq.x, qq.y, qq.z, 0, k, start_count, __int_as_float(0x7f800000), best);
+  int* oi = out_idx + (size_t)i * k;
+  float* od = out_sqd + (size_t)i * k;
+#pragma unroll
+  for (int t = 0; t < K; t++) {
+    if (t < k) {
+      const int p = best.p[t];
+      oi[t] = p >= 0 ? __float_as_int(__ldg(&g.pts[p].w)) : -1;
+      od[t] = p >= 0 ? best.d[t] : __int_as_float(0x7f800000);
+    }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(64) knn_query_dyn_kernel(GridView g, const float4* __restrict__ q, int nq, int k, int start_count,
+                                                          int* __restrict__ out_idx, float* __restrict__ out_sqd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const float4 qq = __ldg(q + i);
+  TopKDyn<KMAX> best;
+  best.cap = k;
+  grid_knn(g, qq.x, qq.y, qq.z, 0, k, start_count, __int_as_float(0x7f800000), best);
+  write_public(g, best, k, k, out_idx + (size_t)i * k, out_sqd + (size_t)i * k);
+}
+
+inline int start_count_for(int k) { return k < 4 ? 1 : (k + 3) / 4; }
+
+}  // namespace
+
+constexpr int kMaxK = 128;
+
+int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term) {
+  if (k < 1 || k > kMaxK) return fail(h, NGICP_ERR_UNSUPPORTED, "k must be in [1,128]");
+  const GridView g = idx->view();
+  const int n = idx->n;
+  const int normalization = ((k - 1) * (2 + k)) / 2;  // integer arithmetic, nano_gicp.cc:345
+  const int sc = start_count_for(k);
+  cudaStream_t s = h->stream;
+#define LAUNCH_SELF(K) knn_self_kernel<K><<<(n + 127) / 128, 128, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term)
+  if (k == 1) LAUNCH_SELF(1);
+  else if (k <= 8) LAUNCH_SELF(8);
+  else if (k <= 16) LAUNCH_SELF(16);
+  else if (k <= 20) LAUNCH_SELF(20);
+  else if (k <= 32) LAUNCH_SELF(32);
+  else knn_self_dyn_kernel<kMaxK><<<(n + 63) / 64, 64, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term);
+#undef LAUNCH_SELF
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  return NGICP_OK;
+}
+
+int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, int* d_out_idx, float* d_out_sqd) {
+  if (k < 1 || k > kMaxK) return fail(h, NGICP_ERR_UNSUPPORTED, "k must be in [1,128]");
+  if (idx->n_seg != 1) return fail(h, NGICP_ERR_UNSUPPORTED, "public k-NN queries need a single-segment index");
+  if (nq <= 0) return NGICP_OK;
+  const GridView g = idx->view();
+  const int sc = start_count_for(k);
+  cudaStream_t s = h->stream;
+#define LAUNCH_Q(K) knn_query_kernel<K><<<(nq + 127) / 128, 128, 0, s>>>(g, d_q, nq, k, sc, d_out_idx, d_out_sqd)
+  if (k == 1) LAUNCH_Q(1);
+  else if (k <= 8) LAUNCH_Q(8);
+  else if (k <= 16) LAUNCH_Q(16);
+  else if (k <= 20) LAUNCH_Q(20);
+  else if (k <= 32) LAUNCH_Q(32);
+  else knn_query_dyn_kernel<kMaxK><<<(nq + 63) / 64, 64, 0, s>>>(g, d_q, nq, k, sc, d_out_idx, d_out_sqd);
+#undef LAUNCH_Q
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  return NGICP_OK;
+}
+
+}  // namespace ngicp

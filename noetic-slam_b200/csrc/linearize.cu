@@ -1,0 +1,462 @@
+// K4 / K5 — fused correspondence search + GICP linearisation, and the cached-correspondence error.
+// Replaces (reference src/dlio/src/nano_gicp/nano_gicp.cc):
+//   update_correspondences :206-245  fp32 transform, 1-NN in the target, distance gate,
+//                                     RCR = C_B + R C_A R^T, Mahalanobis = RCR^-1
+//   linearize              :248-302  e = p_B - T p_A, J = [skew(T p_A) | -I], H += J^T M J, b += J^T M e
+//   compute_error          :305-326  sum e^T M e at a trial pose with the cached correspondences
+// One thread per source point (Morton order, so a warp probes neighbouring target cells). The 21
+// upper-triangular terms of H, the 6 of b, the error and the correspondence count are reduced with
+// warp shuffles, then per block, then by the last block to finish (fixed order => run-to-run
+// deterministic, unlike the reference's per-thread OpenMP partials), with Neumaier-compensated
+// accumulation across blocks. The result lands in host-mapped pinned memory; the host's 6x6 LM
+// solve waits on a sequence number, not on a stream synchronise.
+// compute_error does not cache the Mahalanobis matrices: it rebuilds them from the pose of the last
+// linearize with the very same device function, so both kernels see bit-identical M.
+#include "internal.h"
+#include "linearize.cuh"
+
+namespace ngicp {
+
+namespace {
+
+constexpr int kTerms = 29;  // 21 H + 6 b + error + count(c>0)
+constexpr int kLinThreads = 128;
+
+// symmetric RCR^-1 with explicit fma so K4 and K5 agree bit for bit
+__device__ __forceinline__ void mahalanobis(const PoseArg& P, const float* __restrict__ ca, const float* __restrict__ cb, double M[6]) {
+  const double a00 = ca[0], a01 = ca[1], a02 = ca[2], a11 = ca[3], a12 = ca[4], a22 = ca[5];
+  const double* R = P.R;
+  // T = R * C_A
+  double T[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+    T[3 * r + 0] = __fma_rn(r2, a02, __fma_rn(r1, a01, __dmul_rn(r0, a00)));
+    T[3 * r + 1] = __fma_rn(r2, a12, __fma_rn(r1, a11, __dmul_rn(r0, a01)));
+    T[3 * r + 2] = __fma_rn(r2, a22, __fma_rn(r1, a12, __dmul_rn(r0, a02)));
+  }
+  // RCR = C_B + T R^T (upper triangle)
+  double s[6];
+  const int ri[6] = {0, 0, 0, 1, 1, 2}, ci[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int e = 0; e < 6; e++) {
+    const int r = ri[e], c = ci[e];
+    const double v = __fma_rn(T[3 * r + 2], R[3 * c + 2], __fma_rn(T[3 * r + 1], R[3 * c + 1], __dmul_rn(T[3 * r], R[3 * c])));
+    s[e] = __dadd_rn((double)cb[e], v);
+  }
+  const double xx = s[0], xy = s[1], xz = s[2], yy = s[3], yz = s[4], zz = s[5];
+  const double c00 = __fma_rn(yy, zz, -__dmul_rn(yz, yz));
+  const double c01 = __fma_rn(xz, yz, -__dmul_rn(xy, zz));
+  const double c02 = __fma_rn(xy, yz, -__dmul_rn(xz, yy));
+  const double c11 = __fma_rn(xx, zz, -__dmul_rn(xz, xz));
+  const double c12 = __fma_rn(xy, xz, -__dmul_rn(xx, yz));
+  const double c22 = __fma_rn(xx, yy, -__dmul_rn(xy, xy));
+  const double det = __fma_rn(xz, c02, __fma_rn(xy, c01, __dmul_rn(xx, c00)));
+  const double inv = __ddiv_rn(1.0, det);
+  M[0] = __dmul_rn(c00, inv); M[1] = __dmul_rn(c01, inv); M[2] = __dmul_rn(c02, inv);
+  M[3] = __dmul_rn(c11, inv); M[4] = __dmul_rn(c12, inv); M[5] = __dmul_rn(c22, inv);
+}
+
+// residual e = p_B - (R p_A + t) and q = R p_A + t, fp64 (nano_gicp.cc:266-271)
+__device__ __forceinline__ void residual(const PoseArg& P, const float4& pa, const float4& pb, double q[3], double e[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    q[r] = __dadd_rn(__fma_rn(P.R[3 * r + 2], (double)pa.z, __fma_rn(P.R[3 * r + 1], (double)pa.y, __dmul_rn(P.R[3 * r], (double)pa.x))), P.t[r]);
+  }
+  e[0] = __dsub_rn((double)pb.x, q[0]); e[1] = __dsub_rn((double)pb.y, q[1]); e[2] = __dsub_rn((double)pb.z, q[2]);
+}
+
+__device__ __forceinline__ double quad_form(const double M[6], const double e[3], double Me[3]) {
+  Me[0] = __fma_rn(M[2], e[2], __fma_rn(M[1], e[1], __dmul_rn(M[0], e[0])));
+  Me[1] = __fma_rn(M[4], e[2], __fma_rn(M[3], e[1], __dmul_rn(M[1], e[0])));
+  Me[2] = __fma_rn(M[5], e[2], __fma_rn(M[4], e[1], __dmul_rn(M[2], e[0])));
+  return __fma_rn(e[2], Me[2], __fma_rn(e[1], Me[1], __dmul_rn(e[0], Me[0])));
+}
+
+__device__ __forceinline__ void cross3(const double a[3], double bx, double by, double bz, double o[3]) {
+  o[0] = a[1] * bz - a[2] * by;
+  o[1] = a[2] * bx - a[0] * bz;
+  o[2] = a[0] * by - a[1] * bx;
+}
+
+// Reduce `NT` per-thread doubles over the block, publish the block partial, and let the last
+// block of this batch entry (blockIdx.y) fold all partials (Neumaier) into the result slot.
+template <int NT>
+__device__ __forceinline__ void block_reduce_and_publish(double acc[NT], double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                                         ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  constexpr int kWarps = kLinThreads / 32;
+  __shared__ double sm[kWarps][NT];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    double v = acc[t];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) sm[warp][t] = v;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  double* my = partials + ((size_t)b * gridDim.x + blockIdx.x) * 32;
+  if (threadIdx.x < NT) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) v += sm[w][threadIdx.x];
+    my[threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[b], 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double* all = partials + (size_t)b * gridDim.x * 32;
+  for (int t = warp; t < NT; t += kWarps) {
+    double s = 0.0, c = 0.0;  // Neumaier
+    for (unsigned int i = lane; i < gridDim.x; i += 32) {
+      const double x = __ldcg(all + (size_t)i * 32 + t);
+      const double y = s + x;
+      c += (fabs(s) >= fabs(x)) ? ((s - y) + x) : ((x - y) + s);
+      s = y;
+    }
+    double v = s + c;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) { slots[b].v[t] = v; __threadfence_system(); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counters[b] = 0;  // ready for the next launch
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&slots[b].seq) = seq;
+    __threadfence_system();
+  }
+}
+
+__device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* __restrict__ poses) {
+  if (!poses) return p0;
+  return poses[blockIdx.y];
+}
+
+// K4. grid = (blocks per scan, scans). Source scan b = source segment b; its target segment is
+// target_seg[b] (or 0).
+template <bool WANT_HB>
+__global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
+                                                                 PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ target_seg,
+                                                                 double thr2, float max_sqd, int* __restrict__ corr,
+                                                                 double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                                                 ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  const PoseArg P = load_pose(pose0, poses);
+  const int b = blockIdx.y;
+  const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
+  const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
+  const int tseg = target_seg ? __ldg(target_seg + b) : 0;
+  double acc[kTerms];
+#pragma unroll
+  for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
+
+  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
+    const float4 pa = __ldg(src.pts + j);
+    // fp32 transform of the query, ((r0*x + r1*y) + r2*z) + t*w with w = 1 (nano_gicp.cc:222)
+    float qf[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
+    TopK<1> best;
+    grid_knn(tgt, qf[0], qf[1], qf[2], tseg, 1, 1, max_sqd, best);
+    const int pos = best.p[0];
+    const bool valid = pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
+    corr[j] = valid ? pos : -1;
+    if (!valid) continue;
+    const float4 pb = __ldg(tgt.pts + pos);
+    float ca[6], cb[6];
+    {
+      const float2* a2 = reinterpret_cast<const float2*>(cov_src + (size_t)j * 6);
+      const float2* b2 = reinterpret_cast<const float2*>(cov_tgt + (size_t)pos * 6);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const float2 va = __ldg(a2 + i), vb = __ldg(b2 + i);
+        ca[2 * i] = va.x; ca[2 * i + 1] = va.y; cb[2 * i] = vb.x; cb[2 * i + 1] = vb.y;
+      }
+    }
+    double M[6], q[3], e[3], Me[3];
+    mahalanobis(P, ca, cb, M);
+    residual(P, pa, pb, q, e);
+    acc[27] += quad_form(M, e, Me);
+    acc[28] += (__float_as_int(pb.w) > 0) ? 1.0 : 0.0;  // num_correspondences counts indices > 0 (nano_gicp.cc:244)
+    if (WANT_HB) {
+      // G = S M (S = skew(q)): column k = q x M[:,k];  H_rr row i = q x G[i,:];  H_rt = G;  H_tt = M
+      double g0[3], g1[3], g2[3];
+      cross3(q, M[0], M[1], M[2], g0);
+      cross3(q, M[1], M[3], M[4], g1);
+      cross3(q, M[2], M[4], M[5], g2);
+      // rows of G: G[i][k] = gk[i]
+      double h0[3], h1[3], h2[3];
+      cross3(q, g0[0], g1[0], g2[0], h0);
+      cross3(q, g0[1], g1[1], g2[1], h1);
+      cross3(q, g0[2], g1[2], g2[2], h2);
+      // upper triangle, row-major: (0,0..5) (1,1..5) (2,2..5) (3,3..5) (4,4..5) (5,5)
+      acc[0] += h0[0]; acc[1] += h0[1]; acc[2] += h0[2]; acc[3] += g0[0]; acc[4] += g1[0]; acc[5] += g2[0];
+      acc[6] += h1[1]; acc[7] += h1[2]; acc[8] += g0[1]; acc[9] += g1[1]; acc[10] += g2[1];
+      acc[11] += h2[2]; acc[12] += g0[2]; acc[13] += g1[2]; acc[14] += g2[2];
+      acc[15] += M[0]; acc[16] += M[1]; acc[17] += M[2];
+      acc[18] += M[3]; acc[19] += M[4];
+      acc[20] += M[5];
+      // b = J^T M e = [ -q x Me ; -Me ]
+      double qm[3];
+      cross3(q, Me[0], Me[1], Me[2], qm);
+      acc[21] -= qm[0]; acc[22] -= qm[1]; acc[23] -= qm[2];
+      acc[24] -= Me[0]; acc[25] -= Me[1]; acc[26] -= Me[2];
+    }
+  }
+  block_reduce_and_publish<kTerms>(acc, partials, counters, slots, seq);
+}
+
+// K5. Trial pose P, Mahalanobis rebuilt at the linearisation pose P0.
+__global__ void __launch_bounds__(kLinThreads) error_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
+                                                            PoseArg pose0, const PoseArg* __restrict__ poses, PoseArg lin0, const PoseArg* __restrict__ lins,
+                                                            const int* __restrict__ corr, double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                                            ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  const PoseArg P = load_pose(pose0, poses);
+  const PoseArg P0 = load_pose(lin0, lins);
+  const int b = blockIdx.y;
+  const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
+  const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
+  double acc[1] = {0.0};
+  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
+    const int pos = __ldg(corr + j);
+    if (pos < 0) continue;
+    const float4 pa = __ldg(src.pts + j);
+    const float4 pb = __ldg(tgt.pts + pos);
+    float ca[6], cb[6];
+    const float2* a2 = reinterpret_cast<const float2*>(cov_src + (size_t)j * 6);
+    const float2* b2 = reinterpret_cast<const float2*>(cov_tgt + (size_t)pos * 6);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float2 va = __ldg(a2 + i), vb = __ldg(b2 + i);
+      ca[2 * i] = va.x; ca[2 * i + 1] = va.y; cb[2 * i] = vb.x; cb[2 * i + 1] = vb.y;
+    }
+    double M[6], q[3], e[3], Me[3];
+    mahalanobis(P0, ca, cb, M);
+    residual(P, pa, pb, q, e);
+    acc[0] += quad_form(M, e, Me);
+  }
+  block_reduce_and_publish<1>(acc, partials, counters, slots, seq);
+}
+
+// API-parity export of update_correspondences in ORIGINAL source order (slow path, tests only)
+__global__ void __launch_bounds__(128) export_corr_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
+                                                          PoseArg P, const int* __restrict__ corr_sorted, int* __restrict__ corr_out,
+                                                          float* __restrict__ sqd_out, double* __restrict__ mahal_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= src.n) return;
+  const float4 pa = __ldg(src.pts + j);
+  const int orig = __float_as_int(pa.w);
+  const int pos = corr_sorted[j];
+  if (corr_out) corr_out[orig] = pos >= 0 ? __float_as_int(__ldg(&tgt.pts[pos].w)) : -1;
+  float d = __int_as_float(0x7f800000);
+  double M4[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) M4[i] = 0.0;
+  if (pos >= 0) {
+    const float4 pb = __ldg(tgt.pts + pos);
+    float qf[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
+    d = sqdist_ref(qf[0], qf[1], qf[2], pb.x, pb.y, pb.z);
+    float ca[6], cb[6];
+    for (int i = 0; i < 6; i++) { ca[i] = cov_src[(size_t)j * 6 + i]; cb[i] = cov_tgt[(size_t)pos * 6 + i]; }
+    double M[6];
+    mahalanobis(P, ca, cb, M);
+    M4[0] = M[0]; M4[1] = M[1]; M4[2] = M[2];
+    M4[4] = M[1]; M4[5] = M[3]; M4[6] = M[4];
+    M4[8] = M[2]; M4[9] = M[4]; M4[10] = M[5];
+  }
+  if (sqd_out) sqd_out[orig] = d;
+  if (mahal_out)
+    for (int i = 0; i < 16; i++) mahal_out[(size_t)orig * 16 + i] = M4[i];
+}
+
+__global__ void __launch_bounds__(256) transform_points_kernel(const float* __restrict__ in, int stride, int n, PoseArg P, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[(size_t)i * stride], y = in[(size_t)i * stride + 1], z = in[(size_t)i * stride + 2];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    out[(size_t)i * 3 + r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], x), __fmul_rn(P.Rf[3 * r + 1], y)), __fmul_rn(P.Rf[3 * r + 2], z)), P.tf[r]);
+}
+
+}  // namespace
+
+PoseArg make_pose(const double T[16]) {
+  PoseArg P;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) { P.R[3 * r + c] = T[4 * c + r]; P.Rf[3 * r + c] = (float)T[4 * c + r]; }
+    P.t[r] = T[12 + r];
+    P.tf[r] = (float)T[12 + r];
+  }
+  return P;
+}
+
+static float max_sqd_for(double thr) {
+  // smallest float that is certainly >= thr^2 (so that "covered^2 >= max_sqd" implies nothing unvisited can pass the gate)
+  const double t2 = thr * thr;
+  if (!(t2 < 3.0e38)) return __builtin_inff();
+  float f = (float)t2;
+  f = __builtin_nextafterf(f, __builtin_inff());
+  return __builtin_nextafterf(f, __builtin_inff());
+}
+
+int lin_blocks_for(int n) {
+  const int want = (n + kLinThreads * 2 - 1) / (kLinThreads * 2);  // ~2 points per thread
+  return std::max(1, std::min(want, kMaxLinBlocks));
+}
+
+static int wait_slot(Handle* h, int n_slots, unsigned long long seq) {
+  // spin on the host-mapped sequence numbers; poll the stream every so often so that a failed
+  // launch cannot hang the caller
+  for (int b = 0; b < n_slots; b++) {
+    volatile unsigned long long* p = &h->slot_host[b].seq;
+    unsigned long long spins = 0;
+    while (*p != seq) {
+      if ((++spins & 0x3fff) != 0) continue;
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) return fail(h, NGICP_ERR_CUDA, std::string("reduction kernel: ") + cudaGetErrorString(q));
+      if (*p != seq) return fail(h, NGICP_ERR_CUDA, "reduction kernel finished without writing its result slot");
+    }
+  }
+  __sync_synchronize();
+  return NGICP_OK;
+}
+
+static int check_ready(Handle* h) {
+  for (int w = 0; w < 2; w++) {
+    if (!h->index[w]) return fail(h, NGICP_ERR_INVALID, w == 0 ? "no source cloud" : "no target cloud");
+    if (!h->covs[w].valid || h->covs[w].n != (size_t)h->index[w]->n)
+      return fail(h, NGICP_ERR_INVALID, w == 0 ? "source covariances missing" : "target covariances missing");
+  }
+  return NGICP_OK;
+}
+
+static int ensure_corr(Handle* h, size_t n) {
+  if (h->corr_cap >= n) return NGICP_OK;
+  if (h->corr) NGICP_CUDA(h, cudaFree(h->corr));
+  h->corr = nullptr; h->corr_cap = 0;
+  NGICP_CUDA(h, cudaMalloc(&h->corr, sizeof(int) * n));
+  h->corr_cap = n;
+  return NGICP_OK;
+}
+
+int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
+  if (int rc = check_ready(h)) return rc;
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  if (si->n_seg != 1 || ti->n_seg != 1) return fail(h, NGICP_ERR_UNSUPPORTED, "linearize: use the batch API for multi-segment clouds");
+  if (int rc = ensure_corr(h, si->n)) return rc;
+  const PoseArg P = make_pose(T);
+  const double thr = h->params.max_corr_dist;
+  const double thr2 = thr * thr;
+  const dim3 grid(lin_blocks_for(si->n), 1);
+  const unsigned long long seq = ++h->seq;
+  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+  if (want_Hb)
+    linearize_kernel<true><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
+                                                              max_sqd_for(thr), h->corr, h->partials, h->counter, h->slot_dev, seq);
+  else
+    linearize_kernel<false><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
+                                                               max_sqd_for(thr), h->corr, h->partials, h->counter, h->slot_dev, seq);
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+  if (int rc = wait_slot(h, 1, seq)) return rc;
+  if (h->timing) {
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->t.linearize_ms += ms;
+  }
+  h->t.linearize_calls++;
+  const double* v = h->slot_host[0].v;
+  if (H && b && want_Hb) {
+    int t = 0;
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) { H[6 * r + c] = v[t]; H[6 * c + r] = v[t]; t++; }
+    for (int i = 0; i < 6; i++) b[i] = v[21 + i];
+  }
+  if (err) *err = v[27];
+  h->num_correspondences = (int)(v[28] + 0.5);
+  if (ncorr) *ncorr = h->num_correspondences;
+  for (int i = 0; i < 9; i++) h->lin_pose[i] = P.R[i];
+  for (int i = 0; i < 3; i++) h->lin_pose[9 + i] = P.t[i];
+  h->lin_valid = true;
+  return NGICP_OK;
+}
+
+int compute_error_device(Handle* h, const double T[16], double* err) {
+  if (int rc = check_ready(h)) return rc;
+  if (!h->lin_valid) return fail(h, NGICP_ERR_INVALID, "compute_error before linearize (no cached correspondences)");
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  const PoseArg P = make_pose(T);
+  PoseArg P0;
+  for (int i = 0; i < 9; i++) { P0.R[i] = h->lin_pose[i]; P0.Rf[i] = (float)h->lin_pose[i]; }
+  for (int i = 0; i < 3; i++) { P0.t[i] = h->lin_pose[9 + i]; P0.tf[i] = (float)h->lin_pose[9 + i]; }
+  const dim3 grid(lin_blocks_for(si->n), 1);
+  const unsigned long long seq = ++h->seq;
+  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+  error_kernel<<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, P0, nullptr, h->corr, h->partials,
+                                                   h->counter, h->slot_dev, seq);
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+  if (int rc = wait_slot(h, 1, seq)) return rc;
+  if (h->timing) {
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->t.error_ms += ms;
+  }
+  h->t.error_calls++;
+  if (err) *err = h->slot_host[0].v[0];
+  return NGICP_OK;
+}
+
+int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr) {
+  double e;
+  if (int rc = linearize_device(h, T, false, nullptr, nullptr, &e, ncorr)) return rc;
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  const int n = si->n;
+  cudaStream_t s = h->stream;
+  int* d_corr = nullptr; float* d_sqd = nullptr; double* d_m = nullptr;
+  if (corr) NGICP_CUDA(h, dev_alloc(&d_corr, (size_t)n, s));
+  if (sqd) NGICP_CUDA(h, dev_alloc(&d_sqd, (size_t)n, s));
+  if (mahal) NGICP_CUDA(h, dev_alloc(&d_m, (size_t)n * 16, s));
+  export_corr_kernel<<<(n + 127) / 128, 128, 0, s>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, make_pose(T), h->corr, d_corr, d_sqd, d_m);
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  if (corr) NGICP_CUDA(h, cudaMemcpyAsync(corr, d_corr, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  if (sqd) NGICP_CUDA(h, cudaMemcpyAsync(sqd, d_sqd, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  if (mahal) NGICP_CUDA(h, cudaMemcpyAsync(mahal, d_m, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, s));
+  NGICP_CUDA(h, cudaStreamSynchronize(s));
+  dev_free(d_corr, s); dev_free(d_sqd, s); dev_free(d_m, s);
+  return NGICP_OK;
+}
+
+int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out) {
+  double Td[16];
+  for (int i = 0; i < 16; i++) Td[i] = T[i];
+  PoseArg P = make_pose(Td);
+  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) P.Rf[3 * r + c] = T[4 * c + r]; P.tf[r] = T[12 + r]; }
+  transform_points_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_xyz_in, stride_floats, n, P, d_xyz_out);
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  return NGICP_OK;
+}
+
+}  // namespace ngicp

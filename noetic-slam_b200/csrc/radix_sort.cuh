@@ -1,0 +1,30 @@
+// Stable LSD radix sort of (64-bit voxel key, 32-bit point index) pairs — the "radix-sorted integer
+// keys" step of the Morton/voxel-hash index that replaces the reference's recursive KD-tree build
+// (reference src/dlio/include/nano_gicp/nanoflann.h:1025-1185).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ngicp {
+
+constexpr int kSortRadixBits = 8;
+constexpr int kSortRadix = 1 << kSortRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                                  // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;           // keys per block
+
+inline int sort_num_blocks(int n) { return (n + kSortTile - 1) / kSortTile; }
+inline int sort_num_passes(int nbits) { return (nbits + kSortRadixBits - 1) / kSortRadixBits; }
+// scratch (uint32 elements): per-pass digit starts [passes*256] + per-block counts [256*nblocks]
+inline size_t sort_scratch_elems(int n, int nbits) {
+  return (size_t)sort_num_passes(nbits) * kSortRadix + (size_t)kSortRadix * sort_num_blocks(n) + 64;
+}
+
+// Sorts n pairs by key bits [0, nbits). (keys_a, vals_a) hold the input; (keys_b, vals_b) are
+// ping-pong buffers of the same size. On return *out_keys / *out_vals point at whichever pair
+// holds the sorted result. Returns the number of kernels launched.
+int radix_sort_pairs(unsigned long long* keys_a, uint32_t* vals_a, unsigned long long* keys_b, uint32_t* vals_b,
+                     uint32_t* scratch, int n, int nbits, cudaStream_t stream,
+                     unsigned long long** out_keys, uint32_t** out_vals);
+
+}  // namespace ngicp

@@ -1,0 +1,117 @@
+"""ctypes binding of libngicp_b200.so — the C ABI declared in include/ngicp_b200.h.
+
+The library is the product: hand-written CUDA for sm_100a behind a plain C interface. There is no
+CPU fallback here or in the library; a missing .so or a missing B200 is an error, loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG_ROOT = Path(__file__).resolve().parent.parent          # noetic-slam_b200/
+LIB_PATH = PKG_ROOT / "libngicp_b200.so"
+CSRC = PKG_ROOT / "csrc"
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_LM_NOT_CONVERGED = range(6)
+REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
+SOURCE, TARGET = 0, 1
+
+# every symbol include/ngicp_b200.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "ngicp_default_params", "ngicp_version", "ngicp_last_error", "ngicp_create", "ngicp_destroy", "ngicp_set_params",
+    "ngicp_get_params", "ngicp_stream", "ngicp_synchronize", "ngicp_index_build", "ngicp_index_build_device",
+    "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_index_keys", "ngicp_set_input",
+    "ngicp_attach_index", "ngicp_get_index", "ngicp_swap_source_and_target", "ngicp_clear", "ngicp_compute_covariances",
+    "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
+    "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances",
+    "ngicp_enable_timing", "ngicp_get_timings",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("k_correspondences", C.c_int), ("max_corr_dist", C.c_double), ("regularization", C.c_int),
+                ("max_iterations", C.c_int), ("rotation_epsilon", C.c_double), ("transformation_epsilon", C.c_double),
+                ("lm_init_lambda_factor", C.c_double), ("lm_max_iterations", C.c_int), ("use_gauss_newton", C.c_int)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("index_ms", C.c_float), ("knn_ms", C.c_float), ("covariance_ms", C.c_float), ("linearize_ms", C.c_float),
+                ("error_ms", C.c_float), ("linearize_calls", C.c_int), ("error_calls", C.c_int), ("kernel_launches", C.c_int)]
+
+
+class NgicpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ngicp error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libngicp_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", str(CSRC), "-j8"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libngicp_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback for the CUDA path)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.ngicp_default_params.argtypes = [C.POINTER(Params)]
+    L.ngicp_default_params.restype = None
+    L.ngicp_version.restype = C.c_char_p
+    L.ngicp_last_error.restype = C.c_char_p
+    L.ngicp_last_error.argtypes = [vp]
+    L.ngicp_create.argtypes = [i, C.POINTER(vp)]
+    L.ngicp_destroy.argtypes = [vp]
+    L.ngicp_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.ngicp_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.ngicp_stream.restype = vp
+    L.ngicp_stream.argtypes = [vp]
+    L.ngicp_synchronize.argtypes = [vp]
+    L.ngicp_index_build.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+    L.ngicp_index_build_device.argtypes = [vp, vp, sz, C.POINTER(vp)]
+    L.ngicp_index_retain.argtypes = [vp]
+    L.ngicp_index_release.argtypes = [vp]
+    L.ngicp_index_size.restype = sz
+    L.ngicp_index_size.argtypes = [vp]
+    L.ngicp_knn.argtypes = [vp, vp, vp, sz, sz, i, ip, fp]
+    L.ngicp_index_keys.argtypes = [vp, vp, C.POINTER(C.c_uint64), fp]
+    L.ngicp_set_input.argtypes = [vp, i, vp, sz, sz]
+    L.ngicp_attach_index.argtypes = [vp, i, vp]
+    L.ngicp_get_index.restype = vp
+    L.ngicp_get_index.argtypes = [vp, i]
+    L.ngicp_swap_source_and_target.argtypes = [vp]
+    L.ngicp_clear.argtypes = [vp, i]
+    L.ngicp_compute_covariances.argtypes = [vp, i, fp]
+    L.ngicp_get_covariances.argtypes = [vp, i, dp, sz]
+    L.ngicp_set_covariances.argtypes = [vp, i, dp, sz]
+    L.ngicp_has_covariances.argtypes = [vp, i, C.POINTER(sz)]
+    L.ngicp_update_correspondences.argtypes = [vp, dp, ip, fp, dp, ip]
+    L.ngicp_linearize.argtypes = [vp, dp, dp, dp, dp, ip]
+    L.ngicp_compute_error.argtypes = [vp, dp, dp]
+    L.ngicp_align.argtypes = [vp, fp, fp, ip, ip, dp, dp]
+    L.ngicp_transform_source.argtypes = [vp, fp, vp, sz, sz]
+    L.ngicp_batch_covariances.argtypes = [vp, vp, sz, sz, C.POINTER(C.c_int64), i, dp, fp, fp]
+    L.ngicp_enable_timing.argtypes = [vp, i]
+    L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
+    _lib = L
+    return L
+
+
+def check(handle, rc: int, allow=()):
+    if rc != OK and rc not in allow:
+        msg = lib().ngicp_last_error(handle)
+        raise NgicpError(rc, msg.decode() if msg else "")
+    return rc

@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference interface for the hot path, over the C ABI.
+
+Names, argument meaning and error behaviour follow nano_gicp::NanoGICP<PointSource,PointTarget>
+(reference src/dlio/include/nano_gicp/nano_gicp.h:63-150, src/nano_gicp/nano_gicp.cc) and
+nanoflann::KdTreeFLANN<PointT> (reference include/nano_gicp/nanoflann_adaptor.h:57-152) so that the
+parity tests read like tests of the reference. Clouds are numpy arrays (N, >=3) float32 — the
+reference's 32-byte dlio::Point AoS is `synth.to_aos32(...)`, any stride works. 4x4 matrices are
+ordinary row-major numpy arrays here; the binding transposes to the ABI's column-major.
+
+All compute happens in libngicp_b200.so (CUDA, sm_100a). Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import binding as B
+
+
+def _pts(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError(f"cloud must be (N, >=3) float32, got {a.shape}")
+    return a
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _colmajor64(T) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(T, np.float64).T).reshape(16)
+
+
+class KdTreeFLANN:
+    """nanoflann::KdTreeFLANN<PointT>: setInputCloud builds the Morton/voxel-hash index on the GPU,
+    nearestKSearch is an exact k-NN (rows ordered by distance, then index)."""
+
+    def __init__(self, owner: "NanoGICP | None" = None, device: int = 0):
+        self._L = B.lib()
+        self._owner = owner or NanoGICP(device)
+        self._idx = C.c_void_p(None)
+        self._cloud = None
+
+    @classmethod
+    def _adopt(cls, owner, idx_ptr, cloud):
+        t = cls(owner)
+        t._idx = C.c_void_p(idx_ptr)
+        t._L.ngicp_index_retain(t._idx)
+        t._cloud = cloud
+        return t
+
+    def __del__(self):
+        if getattr(self, "_idx", None) and self._idx.value:
+            self._L.ngicp_index_release(self._idx)
+            self._idx = C.c_void_p(None)
+
+    def setInputCloud(self, cloud):
+        cloud = _pts(cloud)
+        if self._idx.value:
+            self._L.ngicp_index_release(self._idx)
+            self._idx = C.c_void_p(None)
+        h = self._owner._h
+        B.check(h, self._L.ngicp_index_build(h, cloud.ctypes.data, cloud.shape[0], cloud.strides[0], C.byref(self._idx)))
+        self._cloud = cloud
+
+    def getInputCloud(self):
+        return self._cloud
+
+    def size(self) -> int:
+        return int(self._L.ngicp_index_size(self._idx)) if self._idx.value else 0
+
+    def nearestKSearch(self, queries, k: int):
+        """Batched: queries (Q, >=3) -> (k_indices (Q,k) int32, k_sqr_distances (Q,k) float32)."""
+        if not self._idx.value:
+            raise RuntimeError("[nanoflann] findNeighbors() called before building the index.")  # nanoflann.h:1442-1445
+        q = _pts(np.atleast_2d(queries))
+        idx = np.empty((q.shape[0], k), np.int32)
+        sqd = np.empty((q.shape[0], k), np.float32)
+        h = self._owner._h
+        B.check(h, self._L.ngicp_knn(h, self._idx, q.ctypes.data, q.shape[0], q.strides[0], k, _ptr(idx, C.c_int), _ptr(sqd, C.c_float)))
+        return idx, sqd
+
+    def voxel_keys(self):
+        """(keys uint64 (N,) in original point order, origin xyz, h0) — the documented key spec."""
+        n = self.size()
+        keys = np.empty(n, np.uint64)
+        oh = np.zeros(4, np.float32)
+        h = self._owner._h
+        B.check(h, self._L.ngicp_index_keys(h, self._idx, _ptr(keys, C.c_uint64), _ptr(oh, C.c_float)))
+        return keys, oh[:3].copy(), float(oh[3])
+
+
+class NanoGICP:
+    """nano_gicp::NanoGICP<PointT,PointT> on one B200 (one CUDA stream per object)."""
+
+    def __init__(self, device: int = 0):
+        self._L = B.lib()
+        self._h = C.c_void_p(None)
+        B.check(None, self._L.ngicp_create(device, C.byref(self._h)))
+        self._p = B.Params()
+        self._L.ngicp_default_params(C.byref(self._p))
+        self.device = device
+        self._input = None
+        self._target = None
+        self.source_kdtree_ = None
+        self.target_kdtree_ = None
+        self.source_density_ = 0.0
+        self.target_density_ = 0.0
+        self.num_correspondences = 0
+        self.converged_ = False
+        self.nr_iterations_ = 0
+        self.final_transformation_ = np.eye(4, dtype=np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.source_kdtree_ = None
+            self.target_kdtree_ = None
+            self._L.ngicp_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def _push(self):
+        B.check(self._h, self._L.ngicp_set_params(self._h, C.byref(self._p)))
+
+    # ---- setters (nano_gicp.cc:71-94, lsq_registration.cc:73-95) ----
+    def setNumThreads(self, n): pass  # the reference's OpenMP team size has no meaning on the GPU
+    def setCorrespondenceRandomness(self, k): self._p.k_correspondences = int(k); self._push()
+    def setMaxCorrespondenceDistance(self, d): self._p.max_corr_dist = float(d); self._push()
+    def setRegularizationMethod(self, m): self._p.regularization = int(m); self._push()
+    def setMaximumIterations(self, n): self._p.max_iterations = int(n); self._push()
+    def setRotationEpsilon(self, e): self._p.rotation_epsilon = float(e); self._push()
+    def setTransformationEpsilon(self, e): self._p.transformation_epsilon = float(e); self._push()
+    def setInitialLambdaFactor(self, f): self._p.lm_init_lambda_factor = float(f); self._push()
+    def setGaussNewton(self, on=True): self._p.use_gauss_newton = int(bool(on)); self._push()
+
+    # ---- clouds / trees (nano_gicp.cc:97-161) ----
+    def _set_input(self, which, cloud):
+        cloud = _pts(cloud)
+        B.check(self._h, self._L.ngicp_set_input(self._h, which, cloud.ctypes.data, cloud.shape[0], cloud.strides[0]))
+        return KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, which), cloud)
+
+    def setInputSource(self, cloud):
+        if cloud is self._input:      # pointer-identity early-out, nano_gicp.cc:136
+            return
+        self.source_kdtree_ = self._set_input(B.SOURCE, cloud)
+        self._input = cloud
+
+    def setInputTarget(self, cloud):
+        if cloud is self._target:     # nano_gicp.cc:151
+            return
+        self.target_kdtree_ = self._set_input(B.TARGET, cloud)
+        self._target = cloud
+
+    def registerInputSource(self, cloud):  # nano_gicp.cc:119-124: stores the cloud only
+        self._input = cloud
+
+    def registerInputTarget(self, cloud):  # nano_gicp.cc:127-132
+        self._target = cloud
+
+    def setSourceTree(self, tree: KdTreeFLANN):
+        """`source_kdtree_ = tree` (public member assignment in the reference)."""
+        B.check(self._h, self._L.ngicp_attach_index(self._h, B.SOURCE, tree._idx))
+        self.source_kdtree_ = tree
+
+    def setTargetTree(self, tree: KdTreeFLANN):
+        """`gicp.target_kdtree_ = submap_kdtree` (reference src/dlio/odom.cc:995)."""
+        B.check(self._h, self._L.ngicp_attach_index(self._h, B.TARGET, tree._idx))
+        self.target_kdtree_ = tree
+
+    def swapSourceAndTarget(self):
+        B.check(self._h, self._L.ngicp_swap_source_and_target(self._h))
+        self._input, self._target = self._target, self._input
+        self.source_kdtree_, self.target_kdtree_ = self.target_kdtree_, self.source_kdtree_
+
+    def clearSource(self):
+        B.check(self._h, self._L.ngicp_clear(self._h, B.SOURCE)); self._input = None; self.source_kdtree_ = None
+
+    def clearTarget(self):
+        B.check(self._h, self._L.ngicp_clear(self._h, B.TARGET)); self._target = None; self.target_kdtree_ = None
+
+    # ---- covariances (nano_gicp.cc:164-191,330-392) ----
+    def _calc(self, which):
+        d = C.c_float(0)
+        B.check(self._h, self._L.ngicp_compute_covariances(self._h, which, C.byref(d)))
+        return float(d.value)
+
+    def calculateSourceCovariances(self):
+        self.source_density_ = self._calc(B.SOURCE)
+        return True
+
+    def calculateTargetCovariances(self):
+        self.target_density_ = self._calc(B.TARGET)
+        return True
+
+    def _get_covs(self, which):
+        n = C.c_size_t(0)
+        if not self._L.ngicp_has_covariances(self._h, which, C.byref(n)):
+            return None
+        out = np.empty((n.value, 4, 4), np.float64)
+        B.check(self._h, self._L.ngicp_get_covariances(self._h, which, _ptr(out, C.c_double), n.value))
+        return out.transpose(0, 2, 1).copy()
+
+    def getSourceCovariances(self): return self._get_covs(B.SOURCE)
+    def getTargetCovariances(self): return self._get_covs(B.TARGET)
+
+    def _set_covs(self, which, covs):
+        c = np.ascontiguousarray(np.asarray(covs, np.float64).transpose(0, 2, 1))
+        B.check(self._h, self._L.ngicp_set_covariances(self._h, which, _ptr(c, C.c_double), c.shape[0]))
+
+    def setSourceCovariances(self, covs): self._set_covs(B.SOURCE, covs)
+    def setTargetCovariances(self, covs): self._set_covs(B.TARGET, covs)
+
+    # ---- registration (nano_gicp.cc:194-326, lsq_registration.cc:108-229) ----
+    def update_correspondences(self, T):
+        n = self.source_kdtree_.size()
+        corr = np.empty(n, np.int32)
+        sqd = np.empty(n, np.float32)
+        mah = np.empty((n, 4, 4), np.float64)
+        nc = C.c_int(0)
+        t = _colmajor64(T)
+        B.check(self._h, self._L.ngicp_update_correspondences(self._h, _ptr(t, C.c_double), _ptr(corr, C.c_int), _ptr(sqd, C.c_float),
+                                                              _ptr(mah, C.c_double), C.byref(nc)))
+        self.num_correspondences = nc.value
+        return corr, sqd, mah.transpose(0, 2, 1).copy()
+
+    def linearize(self, T):
+        H = np.zeros((6, 6), np.float64)
+        b = np.zeros(6, np.float64)
+        e = C.c_double(0)
+        nc = C.c_int(0)
+        t = _colmajor64(T)
+        B.check(self._h, self._L.ngicp_linearize(self._h, _ptr(t, C.c_double), _ptr(H, C.c_double), _ptr(b, C.c_double), C.byref(e), C.byref(nc)))
+        self.num_correspondences = nc.value
+        return e.value, H, b
+
+    def compute_error(self, T):
+        e = C.c_double(0)
+        t = _colmajor64(T)
+        B.check(self._h, self._L.ngicp_compute_error(self._h, _ptr(t, C.c_double), C.byref(e)))
+        return e.value
+
+    def align(self, guess=None):
+        """pcl::Registration::align(output, guess): returns final_transformation_ (4x4 float32)."""
+        g = None
+        if guess is not None:
+            g = np.ascontiguousarray(np.asarray(guess, np.float32).T).reshape(16)
+        out = np.zeros(16, np.float32)
+        it, conv = C.c_int(0), C.c_int(0)
+        H = np.zeros((6, 6), np.float64)
+        fe = C.c_double(0)
+        rc = self._L.ngicp_align(self._h, _ptr(g, C.c_float) if g is not None else None, _ptr(out, C.c_float), C.byref(it), C.byref(conv),
+                                 _ptr(H, C.c_double), C.byref(fe))
+        B.check(self._h, rc, allow=(B.ERR_LM_NOT_CONVERGED,))  # the reference prints "lm not converged!!" and carries on
+        self.lm_failed_ = rc == B.ERR_LM_NOT_CONVERGED
+        self.final_transformation_ = out.reshape(4, 4).T.copy()
+        self.nr_iterations_ = it.value
+        self.converged_ = bool(conv.value)
+        self.final_hessian_ = H
+        self.final_error_ = fe.value
+        return self.final_transformation_
+
+    def hasConverged(self): return self.converged_
+    def getFinalTransformation(self): return self.final_transformation_
+    def getFinalHessian(self): return self.final_hessian_
+    def getFinalError(self): return self.final_error_
+
+    def transformSource(self, T):
+        """pcl::transformPointCloud(*input_, output, final_transformation_) (lsq_registration.cc:133)."""
+        n = self.source_kdtree_.size()
+        out = np.zeros((n, 3), np.float32)
+        t = np.ascontiguousarray(np.asarray(T, np.float32).T).reshape(16)
+        B.check(self._h, self._L.ngicp_transform_source(self._h, _ptr(t, C.c_float), out.ctypes.data, n, out.strides[0]))
+        return out
+
+    # ---- batched units / instrumentation ----
+    def batchCovariances(self, points, seg_offsets, want_mat4=False):
+        """Covariances of many keyframes in one pass (BASELINE config 3). Returns (cov6 (N,6) float32
+        in original order [, mat4 (N,4,4)], per-keyframe density)."""
+        p = _pts(points)
+        so = np.ascontiguousarray(seg_offsets, np.int64)
+        ns = len(so) - 1
+        cov6 = np.empty((p.shape[0], 6), np.float32)
+        dens = np.empty(ns, np.float32)
+        m4 = np.empty((p.shape[0], 4, 4), np.float64) if want_mat4 else None
+        B.check(self._h, self._L.ngicp_batch_covariances(self._h, p.ctypes.data, p.shape[0], p.strides[0], _ptr(so, C.c_int64), ns,
+                                                         _ptr(m4, C.c_double) if want_mat4 else None, _ptr(cov6, C.c_float), _ptr(dens, C.c_float)))
+        if want_mat4:
+            return cov6, m4.transpose(0, 2, 1).copy(), dens
+        return cov6, dens
+
+    def enableTiming(self, on=True):
+        B.check(self._h, self._L.ngicp_enable_timing(self._h, int(on)))
+
+    def timings(self, reset=True) -> dict:
+        t = B.Timings()
+        B.check(self._h, self._L.ngicp_get_timings(self._h, C.byref(t), int(reset)))
+        return {f: getattr(t, f) for f, _ in B.Timings._fields_}
+
+    def synchronize(self):
+        B.check(self._h, self._L.ngicp_synchronize(self._h))

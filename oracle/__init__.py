@@ -1,0 +1,238 @@
+"""TEST INFRASTRUCTURE — ctypes front-end of the CPU oracle (oracle/oracle.cc).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package, and only as the checker / the reported CPU baseline. The product
+(noetic-slam_b200/) never imports it.
+
+Two shared libraries come out of oracle/oracle.cc (see its header and oracle/Makefile):
+  variant "port" -> oracle/_build/liboracle_port.so  self-contained restatement (own exact k-NN)
+  variant "ref"  -> oracle/_ref/liboracle_ref.so     same restatement over the REFERENCE's own
+                    nanoflann.h, compiled in place from /root/reference (k-NN is reference code)
+Method names mirror nano_gicp::NanoGICP (reference include/nano_gicp/nano_gicp.h:84-137).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIBS = {"port": _HERE / "_build" / "liboracle_port.so", "ref": _HERE / "_ref" / "liboracle_ref.so"}
+_loaded: dict[str, C.CDLL] = {}
+
+REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the oracle. `ref=None` builds the reference variant only when the tree is present."""
+    subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
+    have_ref = Path("/root/reference/src/dlio/include/nano_gicp/nanoflann.h").exists()
+    if ref or (ref is None and have_ref):
+        subprocess.run(["make", "-C", str(_HERE), "-s", "ref"], check=True)
+
+
+def available(variant: str) -> bool:
+    return _LIBS[variant].exists()
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _f64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def lib(variant: str = "port") -> C.CDLL:
+    if variant in _loaded:
+        return _loaded[variant]
+    path = _LIBS[variant]
+    if not path.exists():
+        if variant == "port":
+            build(ref=False)
+        else:
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+    L = C.CDLL(str(path))
+    vp, sz, i, d = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.orc_tree_kind.restype = C.c_char_p
+    L.orc_max_threads.restype = i
+    L.orc_tree_build.restype = vp
+    L.orc_tree_build.argtypes = [fp, sz, sz]
+    L.orc_tree_free.argtypes = [vp]
+    L.orc_knn.restype = i
+    L.orc_knn.argtypes = [vp, fp, sz, sz, i, ip, fp, i, i]
+    L.orc_gicp_create.restype = vp
+    L.orc_gicp_destroy.argtypes = [vp]
+    L.orc_gicp_set_params.argtypes = [vp, i, i, d, i, i, d, d, d, i, i]
+    L.orc_gicp_set_cloud.argtypes = [vp, i, fp, sz, sz]
+    L.orc_gicp_calc_covs.restype = i
+    L.orc_gicp_calc_covs.argtypes = [vp, i, fp]
+    L.orc_gicp_get_covs.restype = sz
+    L.orc_gicp_get_covs.argtypes = [vp, i, dp]
+    L.orc_gicp_set_covs.argtypes = [vp, i, dp, sz]
+    L.orc_gicp_update_correspondences.argtypes = [vp, dp, ip, fp, dp]
+    L.orc_gicp_num_correspondences.restype = i
+    L.orc_gicp_num_correspondences.argtypes = [vp]
+    L.orc_gicp_linearize.restype = d
+    L.orc_gicp_linearize.argtypes = [vp, dp, dp, dp]
+    L.orc_gicp_compute_error.restype = d
+    L.orc_gicp_compute_error.argtypes = [vp, dp]
+    L.orc_gicp_align.restype = i
+    L.orc_gicp_align.argtypes = [vp, fp, fp, ip, ip, dp, dp]
+    _loaded[variant] = L
+    return L
+
+
+def _as_points(p) -> np.ndarray:
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    assert p.ndim == 2 and p.shape[1] >= 3, p.shape
+    return p
+
+
+def _colmajor(T) -> np.ndarray:
+    """4x4 (row-major numpy) -> 16 doubles column-major, what the C ABI takes."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float64).T).reshape(16)
+
+
+class KdTree:
+    """nanoflann::KdTreeFLANN<PointT> stand-in (reference include/nano_gicp/nanoflann_adaptor.h:57-152)."""
+
+    def __init__(self, points, variant: str = "port"):
+        self._L = lib(variant)
+        self._pts = _as_points(points)
+        self._h = self._L.orc_tree_build(_f32p(self._pts), self._pts.shape[0], self._pts.shape[1])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_tree_free(self._h)
+            self._h = None
+
+    def knn(self, queries, k: int, canonical: bool = True, num_threads: int = 0):
+        q = _as_points(queries)
+        idx = np.empty((q.shape[0], k), np.int32)
+        sqd = np.empty((q.shape[0], k), np.float32)
+        self._L.orc_knn(self._h, _f32p(q), q.shape[0], q.shape[1], k, _i32p(idx), _f32p(sqd), int(canonical), num_threads)
+        return idx, sqd
+
+
+class OracleGICP:
+    """CPU restatement of nano_gicp::NanoGICP<PointT,PointT> (reference src/nano_gicp/nano_gicp.cc)."""
+
+    def __init__(self, variant: str = "port", num_threads: int = 0):
+        self._L = lib(variant)
+        self._h = self._L.orc_gicp_create()
+        self.variant = variant
+        self.p = dict(num_threads=num_threads, k=20, max_corr_dist=float(np.finfo(np.float32).max), reg_method=REG_PLANE,
+                      max_iterations=64, rot_eps=2e-3, trans_eps=5e-4, lm_init_lambda_factor=1e-9,
+                      lm_max_iterations=10, gauss_newton=0)
+        self._n = [0, 0]
+        self._push()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_gicp_destroy(self._h)
+            self._h = None
+
+    def _push(self):
+        p = self.p
+        self._L.orc_gicp_set_params(self._h, p["num_threads"], p["k"], p["max_corr_dist"], p["reg_method"], p["max_iterations"],
+                                    p["rot_eps"], p["trans_eps"], p["lm_init_lambda_factor"], p["lm_max_iterations"], p["gauss_newton"])
+
+    # --- setters (names follow the reference) ---
+    def setNumThreads(self, n): self.p["num_threads"] = n; self._push()
+    def setCorrespondenceRandomness(self, k): self.p["k"] = k; self._push()
+    def setMaxCorrespondenceDistance(self, d): self.p["max_corr_dist"] = float(d); self._push()
+    def setRegularizationMethod(self, m): self.p["reg_method"] = int(m); self._push()
+    def setMaximumIterations(self, n): self.p["max_iterations"] = n; self._push()
+    def setRotationEpsilon(self, e): self.p["rot_eps"] = e; self._push()
+    def setTransformationEpsilon(self, e): self.p["trans_eps"] = e; self._push()
+    def setInitialLambdaFactor(self, f): self.p["lm_init_lambda_factor"] = f; self._push()
+
+    def _set_cloud(self, which, pts):
+        pts = _as_points(pts)
+        self._n[which] = pts.shape[0]
+        self._L.orc_gicp_set_cloud(self._h, which, _f32p(pts), pts.shape[0], pts.shape[1])
+
+    def setInputSource(self, pts): self._set_cloud(0, pts)
+    def setInputTarget(self, pts): self._set_cloud(1, pts)
+
+    def _calc(self, which):
+        dens = C.c_float(0)
+        self._L.orc_gicp_calc_covs(self._h, which, C.byref(dens))
+        return float(dens.value)
+
+    def calculateSourceCovariances(self):
+        self.source_density_ = self._calc(0)
+        return True
+
+    def calculateTargetCovariances(self):
+        self.target_density_ = self._calc(1)
+        return True
+
+    def _get_covs(self, which):
+        n = self._L.orc_gicp_get_covs(self._h, which, None)
+        out = np.zeros((n, 4, 4), np.float64)
+        if n:
+            self._L.orc_gicp_get_covs(self._h, which, _f64p(out))
+        return out.transpose(0, 2, 1).copy()  # column-major -> numpy row-major (symmetric anyway)
+
+    def getSourceCovariances(self): return self._get_covs(0)
+    def getTargetCovariances(self): return self._get_covs(1)
+
+    def _set_covs(self, which, covs):
+        c = np.ascontiguousarray(np.asarray(covs, np.float64).transpose(0, 2, 1))
+        self._L.orc_gicp_set_covs(self._h, which, _f64p(c), c.shape[0])
+
+    def setSourceCovariances(self, covs): self._set_covs(0, covs)
+    def setTargetCovariances(self, covs): self._set_covs(1, covs)
+
+    def update_correspondences(self, T):
+        n = self._n[0]
+        corr = np.empty(n, np.int32)
+        sqd = np.empty(n, np.float32)
+        mah = np.empty((n, 4, 4), np.float64)
+        t = _colmajor(T)
+        self._L.orc_gicp_update_correspondences(self._h, _f64p(t), _i32p(corr), _f32p(sqd), _f64p(mah))
+        self.num_correspondences = self._L.orc_gicp_num_correspondences(self._h)
+        return corr, sqd, mah.transpose(0, 2, 1).copy()
+
+    def linearize(self, T):
+        H = np.zeros((6, 6), np.float64)
+        b = np.zeros(6, np.float64)
+        t = _colmajor(T)
+        err = self._L.orc_gicp_linearize(self._h, _f64p(t), _f64p(H), _f64p(b))
+        self.num_correspondences = self._L.orc_gicp_num_correspondences(self._h)
+        return err, H, b
+
+    def compute_error(self, T):
+        t = _colmajor(T)
+        return self._L.orc_gicp_compute_error(self._h, _f64p(t))
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, np.float32)
+        gc = np.ascontiguousarray(g.T).reshape(16)
+        out = np.zeros(16, np.float32)
+        it, conv = C.c_int(0), C.c_int(0)
+        H = np.zeros((6, 6), np.float64)
+        ferr = C.c_double(0)
+        rc = self._L.orc_gicp_align(self._h, _f32p(gc), _f32p(out), C.byref(it), C.byref(conv), _f64p(H), C.byref(ferr))
+        self.final_transformation_ = out.reshape(4, 4).T.copy()
+        self.nr_iterations_ = it.value
+        self.converged_ = bool(conv.value)
+        self.final_hessian_ = H
+        self.final_error_ = ferr.value
+        self.lm_failed_ = bool(rc)
+        return self.final_transformation_
+
+    def hasConverged(self): return self.converged_
+    def getFinalTransformation(self): return self.final_transformation_
+    def getFinalHessian(self): return self.final_hessian_
+    def getFinalError(self): return self.final_error_
