@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the nano_gicp scan-to-map hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): scan-to-submap GICP — one synthetic Ouster OS1-64 scan
+(65,536 points, 1024x64, no voxel filter) registered against a 1,000,000-point concatenated keyframe
+submap whose index and per-keyframe covariances are resident ("covariance reuse",
+reference src/dlio/src/dlio/odom.cc:1719-1738). One STEP = what DLIO does per scan
+(odom.cc:721-722,1005): setInputSource (K1 index build) + calculateSourceCovariances (K2 k-NN, K3
+covariance) + align (K4 linearise / K5 error per LM iteration, 6x6 solve on the host).
+  value : scans/s, scan already in HBM as float4 when the timed region starts (CUDA events on the
+          handle's stream, L2 flushed between steps).
+  e2e   : scans/s through the reference-facing API with HOST buffers (32-byte dlio::Point AoS in,
+          pose out): pack + H2D + kernels + D2H inside the timed region (wall clock around the
+          synchronous call).
+N > 1 (torchrun, one rank per GPU): every rank registers its own sequence against its own submap
+(BASELINE config 5 shape; no data-path collective) — weak scaling, value = total scans/s over the
+max-over-ranks time.
+--impl reference: the CPU oracle (reference nanoflann.h + restated nano_gicp, OpenMP on all host
+cores) on the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "noetic-slam_b200"), str(ROOT / "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_SCAN = 65536
+N_SUBMAP = 1_000_000
+N_KEYFRAMES = 40
+N_DISTINCT_SCANS = 8
+K_CORR = 16
+# algorithmic bytes per unit: compulsory traffic only
+BYTES = {
+    "K1_index_per_pt": 36,        # 16 R + 16 W reordered float4 + 4 W permutation
+    "K2_knn_per_pt": 16 + 4 * K_CORR + 8,   # 16 R + k*4 W neighbour ids + 8 W density term (distances are not materialised)
+    "K3_cov_per_pt": 16 + 4 * K_CORR + 24,  # 104
+    "K4_lin_per_src_pt": 80,      # 16 p_A + 24 C_A + 16 p_B + 24 C_B
+    "K5_err_per_src_pt": 84,      # 16 p_A + 4 corr + 24 C_A + 16 p_B + 24 C_B (Mahalanobis rebuilt, not cached)
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------- data
+def make_workload(seed: int):
+    """(submap (1M,3), keyframe bounds, list of 8 perturbed world-frame scans (65536,3))."""
+    from ngicp import synth
+    sc = synth.Scene(seed)
+    rng = np.random.default_rng(seed + 2)
+    tgt, bounds, poses = synth.make_submap(sc, N_SUBMAP, seed, n_keyframes=N_KEYFRAMES)
+    scans = []
+    for i in range(N_DISTINCT_SCANS):
+        T_ws = poses[(5 + 4 * i) % len(poses)] @ synth.se3((0, 0, 0.02), (0.3, 0.1, 0.0))
+        s = synth.transform_points(T_ws, synth.scan(sc, T_ws, rng, keep_all=True))
+        T_off = synth.random_se3(rng, 0.2, 2.0)        # DLIO hands GICP a scan already close to the map (odom.cc:1005)
+        scans.append(synth.transform_points(np.linalg.inv(T_off), s))
+    return tgt, bounds, scans
+
+
+def configure(g):
+    import scenarios as S
+    return S.configure(g, k=K_CORR, max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)   # cfg/params.yaml:57-63
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arms
+def cpu_register_stream(tgt, bounds, scans, steps, warmup):
+    """The reference's CPU path on the same workload. Returns (scans/s, description)."""
+    import oracle
+    variant = "ref" if oracle.available("ref") else "port"
+    o = configure(oracle.OracleGICP(variant))
+    threads = oracle.lib(variant).orc_max_threads()
+    # submap: per-keyframe covariances computed once and concatenated (covariance reuse), then the tree
+    covs = []
+    for s, e in zip(bounds[:-1], bounds[1:]):
+        o.setInputSource(tgt[s:e]); o.calculateSourceCovariances(); covs.append(o.getSourceCovariances())
+    o.setInputTarget(tgt); o.setTargetCovariances(np.concatenate(covs))
+    ts = []
+    for i in range(warmup + steps):
+        src = scans[i % len(scans)]
+        t0 = time.perf_counter()
+        o.setInputSource(src); o.calculateSourceCovariances(); o.align()
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    kind = "port"   # nano_gicp.cc cannot be compiled here (Eigen/PCL absent); the k-NN inside IS the reference's nanoflann when variant == ref
+    desc = (f"{steps} scan registrations (65,536-pt scan vs 1,000,000-pt submap, k=16) with the oracle "
+            f"({'reference nanoflann.h KD-tree' if variant == 'ref' else 'port k-d tree'} + restated nano_gicp, OpenMP guided,8)")
+    return steps / sum(ts), 1e3 * sum(ts) / steps, threads, kind, desc
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    tgt, bounds, scans = make_workload(0)
+    val, ms, threads, kind, desc = cpu_register_stream(tgt, bounds, scans, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "gicp_scan_to_submap_scans_per_s", "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(1),
+            "cpu_baseline": {"value": val, "unit": "scans/s", "cores": threads, "kind": kind, "sample": desc},
+            "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "cfg2 scan-to-submap GICP: 65,536-pt synthetic OS1-64 scan vs 1,000,000-pt keyframe submap (40 keyframes, covariance reuse), "
+                        "k=16, max_corr 0.5 m, max_iter 32, eps 0.01/0.01; step = setInputSource + calculateSourceCovariances + align",
+            "sequences": world, "parallelism": f"independent sequences x{world} (no collective)",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import ngicp
+    from ngicp import sharding, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t_gen = time.time()
+    tgt, bounds, scans = make_workload(rank)
+    log(f"[rank {rank}] workload generated in {time.time() - t_gen:.1f}s")
+
+    g = configure(ngicp.NanoGICP(local_rank))
+    # submap resident in HBM: per-keyframe covariances in ONE batched pass (reuse), then the 1M-pt index
+    t0 = time.time()
+    _, m4, _ = g.batchCovariances(tgt, bounds, want_mat4=True)
+    g.setInputTarget(tgt)
+    g.setTargetCovariances(m4)
+    g.synchronize()
+    log(f"[rank {rank}] submap index + keyframe covariances resident in {time.time() - t0:.2f}s")
+
+    stream = torch.cuda.ExternalStream(g.stream_ptr(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_scans = []
+    for s in scans:
+        f4 = np.zeros((len(s), 4), np.float32)
+        f4[:, :3] = s
+        d_scans.append(torch.from_numpy(f4).to(dev))
+    h_scans = [synth.to_aos32(s) for s in scans]       # the reference's 32-byte AoS
+    torch.cuda.synchronize()
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = args.warmup, args.steps
+    # ---- value: device-resident input, CUDA events on the handle's stream
+    sampler = ClockSampler(local_rank)
+    iters = []
+    g.timings(reset=True)
+    launches0 = 0
+    dts = []
+    for i in range(W + K):
+        if i == W:
+            barrier()
+            sampler.start()
+            launches0 = g.timings(reset=False)["kernel_launches"]
+        flush_l2()
+        ds = d_scans[i % len(d_scans)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.setInputSourceDevice(ds.data_ptr(), ds.shape[0], token=ds)
+        g.calculateSourceCovariances()
+        g.align()
+        e1.record(stream)
+        e1.synchronize()
+        dts.append(e0.elapsed_time(e1) * 1e-3)
+        iters.append(g.nr_iterations_ + 1)
+    barrier()
+    clocks = sampler.stop()
+    launches = g.timings(reset=False)["kernel_launches"] - launches0
+    t_local = float(sum(dts[W:]))
+    t_max, units = sharding.reduce_job(t_local, float(K), device=dev)
+    value = units / t_max
+
+    # ---- e2e: host buffers through the reference-facing API, wall clock
+    e2e_ts = []
+    for i in range(W + K):
+        if i == W:
+            barrier()
+        flush_l2()
+        hs = h_scans[i % len(h_scans)].copy()          # fresh object every scan, as DLIO's current_scan is (odom.cc:720-723)
+        t0 = time.perf_counter()
+        g.setInputSource(hs)
+        g.calculateSourceCovariances()
+        T = g.align()
+        e2e_ts.append(time.perf_counter() - t0)
+    barrier()
+    e_max, e_units = sharding.reduce_job(float(sum(e2e_ts[W:])), float(K), device=dev)
+    e2e_value = e_units / e_max
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel device times (instrumented pass; not part of the headline numbers)
+    g.enableTiming(True)
+    g.timings(reset=True)
+    reps = 5
+    for i in range(reps):
+        flush_l2()
+        ds = d_scans[i % len(d_scans)]
+        g.setInputSourceDevice(ds.data_ptr(), ds.shape[0], token=ds)
+        g.calculateSourceCovariances()
+        g.align()
+    t = g.timings(reset=True)
+    g.enableTiming(False)
+    hbm = peak_hbm()
+    per = {
+        "K1_index": (t["index_ms"] / reps, BYTES["K1_index_per_pt"] * N_SCAN),
+        "K2_knn": (t["knn_ms"] / reps, BYTES["K2_knn_per_pt"] * N_SCAN),
+        "K3_covariance": (t["covariance_ms"] / reps, BYTES["K3_cov_per_pt"] * N_SCAN),
+        "K4_linearize": (t["linearize_ms"] / max(t["linearize_calls"], 1), BYTES["K4_lin_per_src_pt"] * N_SCAN),
+        "K5_error": (t["error_ms"] / max(t["error_calls"], 1), BYTES["K5_err_per_src_pt"] * N_SCAN),
+    }
+    step_share = {"K1_index": t["index_ms"], "K2_knn": t["knn_ms"], "K3_covariance": t["covariance_ms"], "K4_linearize": t["linearize_ms"],
+                  "K5_error": t["error_ms"]}
+    dominant = max(step_share, key=step_share.get)
+    kernels = {k: {"ms_per_launch": ms, "algorithmic_bytes": b, "GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                   "share_of_step": step_share[k] / max(sum(step_share.values()), 1e-9)} for k, (ms, b) in per.items()}
+    dm, db = per[dominant]
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": db / (dm * 1e-3) / 1e9, "peak": hbm["gbs"], "unit": "GB/s",
+                "frac": db / (dm * 1e-3) / 1e9 / hbm["gbs"], "traffic": None, "peak_source": hbm["source"],
+                "note": "single-scan launches are L2/latency-bound (5 MB per launch); the HBM bar applies to the bulk numbers below"}
+
+    # ---- judged bulk numbers: K3 on a bulk keyframe batch (BASELINE config 3 shape, bounded to 64 keyframes per GPU)
+    bulk = bulk_covariance(g, scans, hbm)
+
+    # ---- CPU baseline beside it (bounded sample, all host cores)
+    cpu_val, cpu_ms, threads, kind, desc = cpu_register_stream(tgt, bounds, scans, 10, 2)
+
+    line = {
+        "metric": "gicp_scan_to_submap_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(world),
+        "ms_per_align_step": 1e3 * t_max / K, "lm_iterations_per_scan": float(np.mean(iters[W:])),
+        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": 1e3 * e_max / K, "h2d_bytes_per_step": N_SCAN * 12,
+                "d2h_bytes_per_step": int(8 + np.mean(iters[W:]) * (29 * 8 + 2 * 8) + 64)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "kernels": kernels, "bulk": bulk,
+        "cpu_baseline": {"value": cpu_val, "unit": "scans/s", "ms_per_step": cpu_ms, "cores": threads, "kind": kind, "sample": desc},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bulk_covariance(g, scans, hbm, n_keyframes=64):
+    """Bulk covariance build: n_keyframes x 65,536 points in one batched pass, every keyframe its own index
+    (BASELINE config 3 shape). Reports K2+K3 throughput and K3's HBM roofline fraction."""
+    from ngicp import synth
+    rng = np.random.default_rng(99)
+    clouds = []
+    for i in range(n_keyframes):
+        T = synth.se3((0, 0, rng.uniform(-np.pi, np.pi)), rng.uniform(-5, 5, 3) * [1, 1, 0.05])
+        clouds.append(synth.transform_points(T, scans[i % len(scans)]))
+    pts = np.concatenate(clouds)
+    off = np.arange(n_keyframes + 1, dtype=np.int64) * N_SCAN
+    g.enableTiming(True)
+    out = {}
+    for rep in range(3):
+        g.timings(reset=True)
+        t0 = time.perf_counter()
+        g.batchCovariances(pts, off)
+        wall = time.perf_counter() - t0
+        t = g.timings(reset=True)
+        out = {"points": int(len(pts)), "keyframes": n_keyframes, "index_ms": t["index_ms"], "knn_ms": t["knn_ms"], "covariance_ms": t["covariance_ms"],
+               "wall_ms_with_h2d_d2h": 1e3 * wall}
+    g.enableTiming(False)
+    n = len(pts)
+    dev_ms = out["index_ms"] + out["knn_ms"] + out["covariance_ms"]
+    out["covariance_mpts_s_device"] = n / (dev_ms * 1e-3) / 1e6
+    k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
+    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": None,
+                          "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
+    return out
+
+
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return {"gbs": float(json.loads(p.read_text())["hbm_gbs"]), "source": "MEASURED_PEAKS.json (of measured)"}
+        except Exception:
+            pass
+    return {"gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    from ngicp import sharding
+    rank, local_rank, world = sharding.world()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29517", str(Path(__file__).resolve()),
+                                   "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)])
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

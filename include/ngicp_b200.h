@@ -103,6 +103,9 @@ int ngicp_index_keys(ngicp_handle* h, const ngicp_index* idx, uint64_t* out_keys
  * DROP existing covariances of that side. The pointer-identity early-out of the reference
  * (:136,:151) lives in the C++ wrapper, which owns the shared_ptr. */
 int ngicp_set_input(ngicp_handle* h, int which, const void* points, size_t n, size_t stride_bytes);
+/* same as ngicp_set_input for a cloud that already lives in device memory as packed float4
+ * (x,y,z,unused); stream-ordered on the handle's stream, no host copy. */
+int ngicp_set_input_device(ngicp_handle* h, int which, const void* d_points_f4, size_t n);
 /* attach an existing index (the `target_kdtree_ = submap_kdtree` assignment, odom.cc:995, and
  * registerInputSource/Target, nano_gicp.cc:119-132). Keeps covariances. Takes its own reference. */
 int ngicp_attach_index(ngicp_handle* h, int which, ngicp_index* idx);

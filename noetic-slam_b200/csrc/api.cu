@@ -407,6 +407,19 @@ ngicp_index* ngicp_get_index(ngicp_handle* p, int which) {
   return wrap(H(p)->index[which]);
 }
 
+static int swap_in_index(Handle* h, int which, Index* idx) {
+  // same stream as everything else this handle does: no synchronisation needed to swap
+  Index* old = h->index[which];
+  h->index[which] = idx;
+  if (old) {
+    if (old->refs.load() == 1) release_index(h, old);                 // sole owner: stream-ordered free
+    else { cudaStreamSynchronize(h->stream); release_index(h, old); } // shared: our reads must be done first
+  }
+  drop_covs(h, which);  // nano_gicp.cc:146,160
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
 int ngicp_set_input(ngicp_handle* p, int which, const void* points, size_t n, size_t stride_bytes) {
   if (!p || (which != 0 && which != 1)) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_input: bad argument");
   Handle* h = H(p);
@@ -418,16 +431,17 @@ int ngicp_set_input(ngicp_handle* p, int which, const void* points, size_t n, si
   const int rc = build_index(h, d_xyz, 3, (int)n, nullptr, 1, &idx);
   dev_free(d_xyz, h->stream);
   if (rc) return rc;
-  // same stream as everything else this handle does: no synchronisation needed to swap
-  Index* old = h->index[which];
-  h->index[which] = idx;
-  if (old) {
-    if (old->refs.load() == 1) release_index(h, old);                 // sole owner: stream-ordered free
-    else { cudaStreamSynchronize(h->stream); release_index(h, old); } // shared: our reads must be done first
-  }
-  drop_covs(h, which);  // nano_gicp.cc:146,160
-  h->lin_valid = false;
-  return NGICP_OK;
+  return swap_in_index(h, which, idx);
+}
+
+int ngicp_set_input_device(ngicp_handle* p, int which, const void* d_points_f4, size_t n) {
+  if (!p || (which != 0 && which != 1)) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_input_device: bad argument");
+  Handle* h = H(p);
+  if (!d_points_f4 || n == 0) return fail(h, NGICP_ERR_INVALID, "ngicp_set_input_device: empty cloud");
+  if (int rc = use_device(h)) return rc;
+  Index* idx = nullptr;
+  if (int rc = build_index(h, static_cast<const float*>(d_points_f4), 4, (int)n, nullptr, 1, &idx)) return rc;
+  return swap_in_index(h, which, idx);
 }
 
 int ngicp_swap_source_and_target(ngicp_handle* p) {

@@ -22,7 +22,7 @@ SOURCE, TARGET = 0, 1
 SYMBOLS = [
     "ngicp_default_params", "ngicp_version", "ngicp_last_error", "ngicp_create", "ngicp_destroy", "ngicp_set_params",
     "ngicp_get_params", "ngicp_stream", "ngicp_synchronize", "ngicp_index_build", "ngicp_index_build_device",
-    "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_index_keys", "ngicp_set_input",
+    "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_index_keys", "ngicp_set_input", "ngicp_set_input_device",
     "ngicp_attach_index", "ngicp_get_index", "ngicp_swap_source_and_target", "ngicp_clear", "ngicp_compute_covariances",
     "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
     "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.ngicp_knn.argtypes = [vp, vp, vp, sz, sz, i, ip, fp]
     L.ngicp_index_keys.argtypes = [vp, vp, C.POINTER(C.c_uint64), fp]
     L.ngicp_set_input.argtypes = [vp, i, vp, sz, sz]
+    L.ngicp_set_input_device.argtypes = [vp, i, vp, sz]
     L.ngicp_attach_index.argtypes = [vp, i, vp]
     L.ngicp_get_index.restype = vp
     L.ngicp_get_index.argtypes = [vp, i]

@@ -152,6 +152,12 @@ class NanoGICP:
         self.target_kdtree_ = self._set_input(B.TARGET, cloud)
         self._target = cloud
 
+    def setInputSourceDevice(self, dev_ptr: int, n: int, token=None):
+        """setInputSource for a scan that is already in HBM as packed float4 (bench's device-resident arm)."""
+        B.check(self._h, self._L.ngicp_set_input_device(self._h, B.SOURCE, C.c_void_p(dev_ptr), n))
+        self.source_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.SOURCE), token)
+        self._input = token
+
     def registerInputSource(self, cloud):  # nano_gicp.cc:119-124: stores the cloud only
         self._input = cloud
 
@@ -296,6 +302,9 @@ class NanoGICP:
         t = B.Timings()
         B.check(self._h, self._L.ngicp_get_timings(self._h, C.byref(t), int(reset)))
         return {f: getattr(t, f) for f, _ in B.Timings._fields_}
+
+    def stream_ptr(self) -> int:
+        return int(self._L.ngicp_stream(self._h) or 0)
 
     def synchronize(self):
         B.check(self._h, self._L.ngicp_synchronize(self._h))

@@ -1,0 +1,54 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/ngicp_b200.h
+declares, and refuses loudly to run without a B200 (no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+import ngicp
+from ngicp import binding as B
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    text = (ROOT / "include" / "ngicp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ngicp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = ngicp.lib()
+    declared = header_functions()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(B.SYMBOLS) == declared
+
+
+def test_default_params_are_the_reference_constructor_defaults():
+    p = B.Params()
+    ngicp.lib().ngicp_default_params(ctypes.byref(p))
+    assert p.k_correspondences == 20 and p.regularization == ngicp.REG_PLANE          # nano_gicp.cc:60,64
+    assert p.max_corr_dist == pytest.approx(3.4028234663852886e38)                      # FLT_MAX, nano_gicp.cc:62
+    assert (p.max_iterations, p.lm_max_iterations) == (64, 10)                           # lsq_registration.cc:55,62
+    assert (p.rotation_epsilon, p.transformation_epsilon, p.lm_init_lambda_factor) == (2e-3, 5e-4, 1e-9)
+
+
+def test_no_cpu_fallback(have_gpu):
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p(None)
+    rc = ngicp.lib().ngicp_create(0, ctypes.byref(h))
+    assert rc == B.ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in ngicp.lib().ngicp_last_error(None)
+    with pytest.raises(ngicp.NgicpError):
+        ngicp.NanoGICP(0)
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"import\s+oracle|from\s+oracle|liboracle|oracle/|orc_[a-z]+\(|#include\s*[<\"].*oracle")
+    for f in (ROOT / "noetic-slam_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h", ".cc") and f.is_file():
+            assert not pat.search(f.read_text()), f

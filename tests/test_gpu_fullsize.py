@@ -1,0 +1,75 @@
+"""GPU tests at BASELINE.json's full sizes (65,536-point OS1-64 scan vs 1,000,000-point submap): parity
+with the oracle where it finishes in seconds, size-independent invariants everywhere else."""
+import numpy as np
+import pytest
+
+import ngicp
+import oracle
+import scenarios as S
+from ngicp import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    sc = synth.Scene(0)
+    rng = np.random.default_rng(2)
+    tgt, bounds, poses = synth.make_submap(sc, 1_000_000, 0, n_keyframes=40)
+    T_ws = poses[20] @ synth.se3((0, 0, 0.02), (0.3, 0.1, 0.0))
+    src = synth.transform_points(T_ws, synth.scan(sc, T_ws, rng, keep_all=True))
+    T_off = synth.se3((0.01, -0.015, 0.03), (0.15, -0.1, 0.05))
+    src = synth.transform_points(np.linalg.inv(T_off), src)
+    assert src.shape == (65536, 3) and tgt.shape == (1_000_000, 3)
+    g = S.configure(ngicp.NanoGICP(0))
+    g.setInputTarget(tgt)
+    g.calculateTargetCovariances()
+    g.setInputSource(src)
+    g.calculateSourceCovariances()
+    return dict(src=src, tgt=tgt, bounds=bounds, T_off=T_off, g=g)
+
+
+def test_knn_1m_against_bruteforce_sample(big):
+    tgt = big["tgt"]
+    tree = big["g"].target_kdtree_
+    rng = np.random.default_rng(0)
+    q = np.concatenate([tgt[rng.choice(len(tgt), 48, replace=False)], big["src"][rng.choice(65536, 48, replace=False)]])
+    idx, sqd = tree.nearestKSearch(q, 16)
+    for i in range(0, len(q), 16):
+        d = (q[i:i + 16, None, :] - tgt[None, :, :]).astype(np.float32)
+        d2 = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]).astype(np.float32)
+        part = np.argpartition(d2, 64, axis=1)[:, :64]
+        pd = np.take_along_axis(d2, part, 1)
+        order = np.lexsort((part, pd), axis=1)[:, :16]
+        assert (np.take_along_axis(part, order, 1) == idx[i:i + 16]).all()
+        assert (np.take_along_axis(pd, order, 1) == sqd[i:i + 16]).all()
+    assert (np.diff(sqd, axis=1) >= 0).all()
+
+
+def test_plane_covariance_invariants_1m(big):
+    """PLANE regularisation: every covariance has spectrum {1, 1, 1e-3} (nano_gicp.cc:372-374)."""
+    C = big["g"].getTargetCovariances()[:, :3, :3]
+    assert not np.isnan(C).any()
+    assert np.abs(np.trace(C, axis1=1, axis2=2) - 2.001).max() < 1e-5
+    assert np.abs(np.linalg.det(C) - 1e-3).max() < 1e-6
+    assert np.abs(C - C.transpose(0, 2, 1)).max() == 0
+
+
+def test_align_65k_vs_1m_matches_oracle_and_truth(big):
+    g = big["g"]
+    T = g.align()
+    assert g.hasConverged()
+    o = S.configure(oracle.OracleGICP("port"))
+    o.setInputTarget(big["tgt"]); o.setInputSource(big["src"])
+    To = o.align()
+    assert g.nr_iterations_ == o.nr_iterations_
+    assert np.abs(T[:3, 3] - To[:3, 3]).max() < 1e-4
+    D = T[:3, :3].astype(np.float64).T @ To[:3, :3].astype(np.float64) - np.eye(3)
+    assert np.linalg.norm(D) / np.sqrt(2.0) < 1e-5            # rotation angle (robust to float32 rounding of the outputs)
+    assert np.abs(T[:3, 3] - big["T_off"][:3, 3]).max() < 0.01      # and it undoes the applied offset
+    # idempotence: starting from the answer, the correction is (close to) nothing
+    T2 = g.align(T)
+    assert np.abs(T2 - T).max() < 5e-3
+    # the optimum beats its neighbourhood under the cached-correspondence error
+    e0, _, _ = g.linearize(T.astype(np.float64))
+    assert e0 <= g.compute_error(synth.se3((0, 0, 0.002), (0.01, 0, 0)) @ T.astype(np.float64))

@@ -1,0 +1,17 @@
+"""Small driver for ncu: resident 1M-pt submap, then a few scan registrations (the bench step)."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "noetic-slam_b200"), str(ROOT / "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import bench, ngicp
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+tgt, bounds, scans = bench.make_workload(0)
+g = bench.configure(ngicp.NanoGICP(0))
+_, m4, _ = g.batchCovariances(tgt, bounds, want_mat4=True)
+g.setInputTarget(tgt); g.setTargetCovariances(m4)
+for i in range(steps):
+    g.setInputSource(scans[i % len(scans)].copy()); g.calculateSourceCovariances(); T = g.align()
+print("iters", g.nr_iterations_, "launches", g.timings()["kernel_launches"])
