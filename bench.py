@@ -89,9 +89,13 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:   # nvidia-smi needs a moment to come up
+                time.sleep(0.01)
+            self.skip = len(self.rows)                        # samples before the timed region are dropped
         except Exception:
             self.proc = None
 
@@ -101,7 +105,9 @@ class ClockSampler:
 
     def stop(self):
         if self.proc:
+            time.sleep(0.06)                                  # let the sample covering the end of the region land
             self.proc.terminate()
+        self.rows = self.rows[getattr(self, "skip", 0):] or self.rows[-1:]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -207,8 +213,8 @@ def run_gpu(args, rank, local_rank, world):
     dts = []
     for i in range(W + K):
         if i == W:
-            barrier()
             sampler.start()
+            barrier()
             launches0 = g.timings(reset=False)["kernel_launches"]
         flush_l2()
         ds = d_scans[i % len(d_scans)]
@@ -222,7 +228,6 @@ def run_gpu(args, rank, local_rank, world):
         dts.append(e0.elapsed_time(e1) * 1e-3)
         iters.append(g.nr_iterations_ + 1)
     barrier()
-    clocks = sampler.stop()
     launches = g.timings(reset=False)["kernel_launches"] - launches0
     t_local = float(sum(dts[W:]))
     t_max, units = sharding.reduce_job(t_local, float(K), device=dev)
@@ -241,6 +246,7 @@ def run_gpu(args, rank, local_rank, world):
         T = g.align()
         e2e_ts.append(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop()     # sampled across both timed regions (device-resident loop and host-buffer loop)
     e_max, e_units = sharding.reduce_job(float(sum(e2e_ts[W:])), float(K), device=dev)
     e2e_value = e_units / e_max
 

@@ -121,8 +121,20 @@ __device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float 
 // (pts[pos].w) is only fetched to break exact distance ties.
 template <int K>
 struct TopK {
+  static constexpr int kK = K;
   float d[K];
   int p[K];
+  // shift register: drop d[0], append at the back (static indices only)
+  __device__ __forceinline__ void append_shift(float dn, int pn) {
+#pragma unroll
+    for (int i = 0; i + 1 < K; i++) { d[i] = d[i + 1]; p[i] = p[i + 1]; }
+    d[K - 1] = dn; p[K - 1] = pn;
+  }
+  __device__ __forceinline__ void pop_front() {
+#pragma unroll
+    for (int i = 0; i + 1 < K; i++) { d[i] = d[i + 1]; p[i] = p[i + 1]; }
+    d[K - 1] = __int_as_float(0x7f800000); p[K - 1] = -1;
+  }
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < K; i++) { d[i] = __int_as_float(0x7f800000); p[i] = -1; }
@@ -134,8 +146,8 @@ struct TopK {
     if (pa < 0) return false;
     return __float_as_int(__ldg(&pts[pa].w)) < __float_as_int(__ldg(&pts[pb].w));
   }
-  __device__ __forceinline__ void offer(float dn, int pn, const float4* __restrict__ pts) {
-    if (dn > d[K - 1]) return;
+  // slow path: full (distance, original index) ordering, only taken when a distance is exactly tied
+  __device__ __forceinline__ void offer_tied(float dn, int pn, const float4* __restrict__ pts) {
     if (!before(dn, pn, d[K - 1], p[K - 1], pts)) return;
     d[K - 1] = dn; p[K - 1] = pn;
 #pragma unroll
@@ -146,6 +158,24 @@ struct TopK {
       }
     }
   }
+  // fast path: rank-and-shift with independent selects (no dependent compare-swap chain)
+  __device__ __forceinline__ void offer(float dn, int pn, const float4* __restrict__ pts) {
+    if (dn > d[K - 1]) return;
+    bool tie = false;
+#pragma unroll
+    for (int i = 0; i < K; i++) tie |= (d[i] == dn);
+    if (tie) { offer_tied(dn, pn, pts); return; }
+#pragma unroll
+    for (int i = K - 1; i > 0; i--) {
+      const bool lti = d[i] < dn, ltm = d[i - 1] < dn;
+      d[i] = lti ? d[i] : (ltm ? dn : d[i - 1]);
+      p[i] = lti ? p[i] : (ltm ? pn : p[i - 1]);
+    }
+    const bool lt0 = d[0] < dn;
+    d[0] = lt0 ? d[0] : dn;
+    p[0] = lt0 ? p[0] : pn;
+  }
+  __device__ __forceinline__ float worst() const { return d[K - 1]; }
   __device__ __forceinline__ float kth(int k) const {  // k in 1..K
     float v = d[K - 1];
 #pragma unroll
@@ -171,6 +201,7 @@ struct TopKDyn {
     while (i > 0 && TopK<1>::before(dn, pn, d[i - 1], p[i - 1], pts)) { d[i] = d[i - 1]; p[i] = p[i - 1]; i--; }
     d[i] = dn; p[i] = pn;
   }
+  __device__ __forceinline__ float worst() const { return d[cap - 1]; }
   __device__ __forceinline__ float kth(int k) const { return d[k - 1]; }
 };
 
@@ -256,7 +287,7 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
     }
     const float covered = fmaxf(gap - margin, 0.0f);
     const float cov2 = covered * covered * 0.999999f;
-    if (best.kth(k) < cov2) break;   // every unvisited point is strictly farther than the k-th best
+    if (best.worst() < cov2) break;   // every unvisited point is strictly farther than the k-th best
     if (cov2 >= max_sqd) break;      // nothing unvisited can be within the correspondence radius
   }
 }

@@ -70,6 +70,9 @@ struct ngicp_handle {
   cudaEvent_t stage_done = nullptr;  // last H2D out of stage_host
   double* batch_partials = nullptr;  // batched reductions (allocated on first use)
   size_t batch_partials_cap = 0;
+  // tuning knobs (env NGICP_K4_CMAX / NGICP_K2_CMAX_MULT override)
+  int k4_cmax = 64;
+  int k2_cmax_mult = 4;
   // LM state (lsq_registration.h:151-168)
   double lm_lambda = -1.0;
   double final_hessian[36];

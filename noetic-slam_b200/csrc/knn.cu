@@ -6,6 +6,7 @@
 // Distances are the reference's fp32 metric bit for bit (common.cuh: sqdist_ref); result rows are
 // ordered by (distance, original index).
 #include "internal.h"
+#include "wknn.cuh"
 
 namespace ngicp {
 
@@ -36,6 +37,36 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
   }
   if (dens_term) {
     // nano_gicp.cc:345-346: accumulate(k_sq_distances.begin()+1, end, 0.0) / normalization
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 1; i < K; i++) if (i < k) acc += (double)best.d[i];
+    dens_term[j] = acc / (double)normalization;
+  }
+}
+
+// Production K2: one warp per 32 consecutive (Morton-sorted) points, shared staged candidates (wknn.cuh).
+constexpr int kSelfWarps = 4;
+template <int K>
+__global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int start_count, int normalization,
+                                                                        int* __restrict__ nbr, double* __restrict__ dens_term) {
+  __shared__ WarpScratch scratch[kSelfWarps];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = j < g.n;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  int seg = 0;
+  if (active) { q = __ldg(g.pts + j); seg = find_segment(g.seg_start, g.n_seg, j); }
+  TopK<K> best;
+  warp_knn(g, active, q.x, q.y, q.z, seg, k, start_count, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5]);
+  if (!active) return;
+  int* row = nbr + (size_t)j * k;
+  if (k == K && (K % 4) == 0) {
+#pragma unroll
+    for (int i = 0; i < K; i += 4) reinterpret_cast<int4*>(row)[i / 4] = make_int4(best.p[i], best.p[i + 1], best.p[i + 2], best.p[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; i++) if (i < k) row[i] = best.p[i];
+  }
+  if (dens_term) {
     double acc = 0.0;
 #pragma unroll
     for (int i = 1; i < K; i++) if (i < k) acc += (double)best.d[i];
@@ -103,6 +134,9 @@ __global__ void __launch_bounds__(64) knn_query_dyn_kernel(GridView g, const flo
 }
 
 inline int start_count_for(int k) { return k < 4 ? 1 : (k + 3) / 4; }
+// group-cell capacity of the warp-cooperative search: large enough that the k-th neighbour of a member
+// lies inside the staged block (block reach >= half the group cell), small enough to keep the scan short
+inline int group_cap_for(int k, int mult) { return k * mult > 32 ? k * mult : 32; }
 
 }  // namespace
 
@@ -115,7 +149,7 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   const int normalization = ((k - 1) * (2 + k)) / 2;  // integer arithmetic, nano_gicp.cc:345
   const int sc = start_count_for(k);
   cudaStream_t s = h->stream;
-#define LAUNCH_SELF(K) knn_self_kernel<K><<<(n + 127) / 128, 128, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term)
+#define LAUNCH_SELF(K) knn_self_warp_kernel<K><<<(n + 32 * kSelfWarps - 1) / (32 * kSelfWarps), 32 * kSelfWarps, 0, s>>>(g, k, group_cap_for(k, h->k2_cmax_mult), normalization, d_nbr, d_dens_term)
   if (k == 1) LAUNCH_SELF(1);
   else if (k <= 8) LAUNCH_SELF(8);
   else if (k <= 16) LAUNCH_SELF(16);
@@ -149,3 +183,12 @@ int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, i
 }
 
 }  // namespace ngicp
+
+#ifdef NGICP_STATS
+extern "C" int ngicp_debug_stats_knn(unsigned long long out[8], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_wknn_stats, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ngicp::g_wknn_stats, z, sizeof z); }
+  return 0;
+}
+#endif

@@ -14,6 +14,7 @@
 // linearize with the very same device function, so both kernels see bit-identical M.
 #include "internal.h"
 #include "linearize.cuh"
+#include "wknn.cuh"
 
 namespace ngicp {
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* _
 template <bool WANT_HB>
 __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
                                                                  PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ target_seg,
-                                                                 double thr2, float max_sqd, int* __restrict__ corr,
+                                                                 double thr2, float max_sqd, int cmax, int* __restrict__ corr,
                                                                  double* __restrict__ partials, unsigned int* __restrict__ counters,
                                                                  ReduceSlot* __restrict__ slots, unsigned long long seq) {
   const PoseArg P = load_pose(pose0, poses);
@@ -158,18 +159,23 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
 #pragma unroll
   for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
 
-  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
-    const float4 pa = __ldg(src.pts + j);
+  __shared__ WarpScratch scratch[kLinThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform trip count: the whole warp runs the cooperative search together (wknn.cuh)
+  for (int j0 = begin + blockIdx.x * kLinThreads + warp * 32; j0 < end; j0 += gridDim.x * kLinThreads) {
+    const int j = j0 + lane;
+    const bool active = j < end;
+    const float4 pa = active ? __ldg(src.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     // fp32 transform of the query, ((r0*x + r1*y) + r2*z) + t*w with w = 1 (nano_gicp.cc:222)
     float qf[3];
 #pragma unroll
     for (int r = 0; r < 3; r++)
       qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
     TopK<1> best;
-    grid_knn(tgt, qf[0], qf[1], qf[2], tseg, 1, 1, max_sqd, best);
+    warp_knn(tgt, active, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
     const int pos = best.p[0];
-    const bool valid = pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
-    corr[j] = valid ? pos : -1;
+    const bool valid = active && pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
+    if (active) corr[j] = valid ? pos : -1;
     if (!valid) continue;
     const float4 pb = __ldg(tgt.pts + pos);
     float ca[6], cb[6];
@@ -312,7 +318,7 @@ static float max_sqd_for(double thr) {
 }
 
 int lin_blocks_for(int n) {
-  const int want = (n + kLinThreads * 2 - 1) / (kLinThreads * 2);  // ~2 points per thread
+  const int want = (n + kLinThreads - 1) / kLinThreads;  // one point per thread: the search is latency-bound, spread it wide
   return std::max(1, std::min(want, kMaxLinBlocks));
 }
 
@@ -366,10 +372,10 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
   if (want_Hb)
     linearize_kernel<true><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
-                                                              max_sqd_for(thr), h->corr, h->partials, h->counter, h->slot_dev, seq);
+                                                              max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq);
   else
     linearize_kernel<false><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
-                                                               max_sqd_for(thr), h->corr, h->partials, h->counter, h->slot_dev, seq);
+                                                               max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq);
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);
@@ -460,3 +466,12 @@ int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats,
 }
 
 }  // namespace ngicp
+
+#ifdef NGICP_STATS
+extern "C" int ngicp_debug_stats_lin(unsigned long long out[8], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_wknn_stats, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ngicp::g_wknn_stats, z, sizeof z); }
+  return 0;
+}
+#endif

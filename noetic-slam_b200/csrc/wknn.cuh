@@ -1,0 +1,280 @@
+// Warp-cooperative exact k-NN over the voxel hash: the production search of K2 (covariance k-NN) and
+// K4 (correspondences). Replaces the per-query KD-tree descent of the reference
+// (src/dlio/include/nano_gicp/nanoflann.h:1587-1666, called from nano_gicp.cc:224,343).
+//
+// A warp owns 32 consecutive queries (Morton order => spatially coherent). Repeatedly:
+//   1. the first unresolved lane leads. Twelve lanes probe the leader's ancestor cells at all
+//      levels at once; the group cell is the LARGEST ancestor holding <= cmax points (never finer
+//      than the level a lane was already refused at, never coarser than the search radius needs);
+//   2. every unresolved lane inside that group cell joins;
+//   3. the 4x4x4 block of half-size cells around the group cell (its 8 children plus one ring) is
+//      staged into shared memory: 64 hash probes, two per lane, then coalesced copies of the
+//      (contiguous, Morton-sorted) voxel buckets, children first;
+//   4. all members scan the SAME staged candidates from shared memory (broadcast reads, no per-lane
+//      global gathers, no trip-count divergence), top-k in registers;
+//   5. the block contains the 3x3x3 neighbourhood of every member's own half-size cell, so the
+//      exactness proof of common.cuh:grid_knn carries over: a member is done when its k-th best is
+//      closer than the nearest block face that still has grid behind it; otherwise it asks for a
+//      coarser group next time.
+#pragma once
+#include "common.cuh"
+
+namespace ngicp {
+
+constexpr int kWarpChunk = 128;  // candidates staged per pass and warp
+
+#ifdef NGICP_STATS
+// development counters: [0] passes, [1] staged candidates, [2] member lanes, [3] warp_knn calls, [4] refused members
+static __device__ unsigned long long g_wknn_stats[8];
+#define WKNN_STAT(i, v) do { const unsigned long long _sv = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_wknn_stats[i], _sv); } while (0)
+#else
+#define WKNN_STAT(i, v) do { } while (0)
+#endif
+
+struct WarpScratch {
+  float4 pts[kWarpChunk];
+  int pos[kWarpChunk];
+  uint32_t rstart[64];
+  uint32_t rpre[65];
+  uint32_t pad[3];
+};
+
+// block cells in scan order: the 8 children of the group cell first (they hold the nearest candidates,
+// so the top-k threshold tightens early and later candidates rarely insert), then the surrounding ring.
+// entry = (ox+1) | (oy+1)<<2 | (oz+1)<<4 with offsets o in [-1,2] relative to the group cell's first child.
+__device__ __constant__ unsigned char kBlockOrder[64] = {
+    0x15, 0x16, 0x19, 0x1a, 0x25, 0x26, 0x29, 0x2a,
+    0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x06, 0x07, 0x08, 0x09, 0x0a, 0x0b, 0x0c, 0x0d, 0x0e, 0x0f,
+    0x10, 0x11, 0x12, 0x13, 0x14, 0x17, 0x18, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f,
+    0x20, 0x21, 0x22, 0x23, 0x24, 0x27, 0x28, 0x2b, 0x2c, 0x2d, 0x2e, 0x2f,
+    0x30, 0x31, 0x32, 0x33, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x3b, 0x3c, 0x3d, 0x3e, 0x3f};
+
+// copy candidates [c0, c0+nch) of the concatenated bucket list into shared memory; returns the range cursor
+__device__ __forceinline__ int wknn_stage_chunk(const GridView& g, WarpScratch& ws, int lane, uint32_t c0, int nch, int r) {
+  for (int e = lane; e < nch; e += 32) {
+    const uint32_t ge = c0 + e;
+    while (ws.rpre[r + 1] <= ge) r++;
+    const int gp = (int)(ws.rstart[r] + (ge - ws.rpre[r]));
+    ws.pts[e] = __ldg(g.pts + gp);
+    ws.pos[e] = gp;
+  }
+  __syncwarp();
+  return r;
+}
+
+template <class TK>
+__device__ __forceinline__ void warp_knn(const GridView& g, bool active, float qx, float qy, float qz, int seg, int k, int cmax,
+                                         float max_sqd, TK& best, WarpScratch& ws) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const GridMeta* __restrict__ m = g.meta;
+  const float h0 = __ldg(&m->h0), inv_h0 = __ldg(&m->inv_h0), margin = __ldg(&m->margin);
+  const int base = __ldg(&m->base_level);
+  if (!active) seg = 0;
+  const float4 o = __ldg(g.seg_origin + seg);
+  const float ux = __fsub_rn(qx, o.x), uy = __fsub_rn(qy, o.y), uz = __fsub_rn(qz, o.z);
+  const int c0x = voxel_coord_unclamped(qx, o.x, inv_h0);
+  const int c0y = voxel_coord_unclamped(qy, o.y, inv_h0);
+  const int c0z = voxel_coord_unclamped(qz, o.z, inv_h0);
+
+  // coarsest level the search radius can ever need: one block at L_reach covers max_sqd
+  int L_reach = base;
+  for (; L_reach < kTopLevel; L_reach++) {
+    const float reach = h0 * (float)(1 << L_reach) - margin;
+    if (reach * reach * 0.999999f >= max_sqd) break;
+  }
+
+  int Lmin = base;  // finest group level this lane still accepts
+  bool done = !active;
+  best.reset();
+  WKNN_STAT(3, 1);
+
+  for (;;) {
+    const unsigned un = __ballot_sync(FULL, !done);
+    if (!un) break;
+    const int leader = __ffs(un) - 1;
+    const int lcx = __shfl_sync(FULL, c0x, leader), lcy = __shfl_sync(FULL, c0y, leader), lcz = __shfl_sync(FULL, c0z, leader);
+    const int sg = __shfl_sync(FULL, seg, leader);
+    const int lLmin = __shfl_sync(FULL, Lmin, leader);
+    const unsigned long long sgbits = (unsigned long long)sg << kMortonBits;
+
+    // ---- 1. group level: largest ancestor of the leader (levels base+1 .. top) with <= cmax points
+    int Lg;
+    {
+      const int P = base + 1 + lane;
+      bool ok = false;
+      if (P <= kTopLevel) {
+        const int maxcP = kMaxCoord >> P;
+        const unsigned int ax = clampi(lcx >> P, 0, maxcP), ay = clampi(lcy >> P, 0, maxcP), az = clampi(lcz >> P, 0, maxcP);
+        const unsigned long long ck = (((sgbits >> (3 * P)) | morton3(ax, ay, az)) << 4) | (unsigned)P;
+        uint32_t s = 0, e = 0;
+        const bool hit = cell_lookup(g.table, g.table_mask, ck, s, e);
+        ok = !hit || (int)(e - s) <= cmax;
+      }
+      const unsigned okm = __ballot_sync(FULL, ok);
+      // counts grow with the level, so the ok lanes form a prefix; take its last lane
+      const int nprefix = __ffs(~okm) - 1;          // number of leading ok lanes (0..12)
+      Lg = base + (nprefix > 0 ? nprefix - 1 : 0) ;  // group cell level P = Lg + 1
+      Lg = max(Lg, lLmin);
+      Lg = min(Lg, max(L_reach, lLmin));
+      Lg = min(Lg, kTopLevel);
+    }
+
+    const int maxc = kMaxCoord >> Lg;
+    const int px = clampi(c0x >> Lg, 0, maxc) >> 1, py = clampi(c0y >> Lg, 0, maxc) >> 1, pz = clampi(c0z >> Lg, 0, maxc) >> 1;
+    const int lpx = __shfl_sync(FULL, px, leader), lpy = __shfl_sync(FULL, py, leader), lpz = __shfl_sync(FULL, pz, leader);
+    const bool member = !done && Lmin <= Lg && seg == sg && px == lpx && py == lpy && pz == lpz;
+
+    // ---- 3. 64 hash probes, two per lane; ranges + exclusive prefix of their sizes into shared memory
+    const unsigned long long sgL = sgbits >> (3 * Lg);
+    uint32_t cnt[2];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int ci = lane + 32 * half;
+      const unsigned code = kBlockOrder[ci];
+      const int ax = 2 * lpx + (int)(code & 3) - 1, ay = 2 * lpy + (int)((code >> 2) & 3) - 1, az = 2 * lpz + (int)((code >> 4) & 3) - 1;
+      uint32_t s = 0, e = 0;
+      if (ax >= 0 && ax <= maxc && ay >= 0 && ay <= maxc && az >= 0 && az <= maxc) {
+        const unsigned long long ck = ((sgL | morton3((unsigned)ax, (unsigned)ay, (unsigned)az)) << 4) | (unsigned)Lg;
+        if (!cell_lookup(g.table, g.table_mask, ck, s, e)) { s = 0; e = 0; }
+      }
+      ws.rstart[ci] = s;
+      cnt[half] = e - s;
+    }
+    uint32_t inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t a = __shfl_up_sync(FULL, inc0, off), b = __shfl_up_sync(FULL, inc1, off);
+      if (lane >= off) { inc0 += a; inc1 += b; }
+    }
+    const uint32_t tot0 = __shfl_sync(FULL, inc0, 31);
+    const uint32_t M = tot0 + __shfl_sync(FULL, inc1, 31);
+    ws.rpre[lane] = inc0 - cnt[0];
+    ws.rpre[lane + 32] = tot0 + inc1 - cnt[1];
+    if (lane == 0) ws.rpre[64] = M;
+    __syncwarp();
+    if (member) best.reset();
+    WKNN_STAT(0, 1); WKNN_STAT(1, M); WKNN_STAT(2, __popc(__ballot_sync(FULL, member)));
+#ifdef NGICP_STATS
+    if (lane == 0) { atomicMax(&g_wknn_stats[5], (unsigned long long)M); if (M > 2048) { atomicAdd(&g_wknn_stats[6], 1ull); atomicAdd(&g_wknn_stats[7], (unsigned long long)M); } }
+#endif
+
+    // ---- 3b/4. stage buckets chunk by chunk and scan them. Three modes:
+    //   shared      : every member scans every staged candidate (cost ~ M per lane, whatever the member count)
+    //   split, k=1  : the 32 lanes split each chunk, one warp-argmin per member and chunk (cost ~ members*M/32)
+    //   split, k>1  : per member, the lanes split all candidates into private top-k lists that are merged by
+    //                 K rounds of warp-argmin; pays off for the heavy tail (few members, thousands of candidates)
+    const unsigned mem_mask = __ballot_sync(FULL, member);
+    const int nmem = __popc(mem_mask);
+    if (TK::kK == 1) {
+      int r = 0;
+      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
+        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
+        r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+        float4 cand[kWarpChunk / 32];
+#pragma unroll
+        for (int t = 0; t < kWarpChunk / 32; t++) cand[t] = ws.pts[min(lane + 32 * t, nch - 1)];
+        unsigned rem = mem_mask;
+        while (rem) {
+          const int mi = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
+          float bd = __int_as_float(0x7f800000);
+          int be = -1;
+#pragma unroll
+          for (int t = 0; t < kWarpChunk / 32; t++) {
+            const int e = lane + 32 * t;
+            const float d = sqdist_ref(mx, my, mz, cand[t].x, cand[t].y, cand[t].z);
+            if (e < nch && d < bd) { bd = d; be = e; }
+          }
+          int bp = be >= 0 ? ws.pos[be] : -1;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(FULL, bd, off);
+            const int op = __shfl_xor_sync(FULL, bp, off);
+            if (TK::before(od, op, bd, bp, g.pts)) { bd = od; bp = op; }
+          }
+          if (lane == mi && bp >= 0 && bd <= best.worst()) best.offer(bd, bp, g.pts);
+        }
+        __syncwarp();
+      }
+    } else if ((long long)nmem * (3ll * M + 1000) < 60ll * M) {
+      unsigned rem = mem_mask;
+      while (rem) {
+        const int mi = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
+        TK part;
+        part.reset();
+        int r = 0;
+        for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
+          const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
+          r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+          for (int e = lane; e < nch; e += 32) {
+            const float4 p = ws.pts[e];
+            const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
+            if (d <= part.worst()) part.offer(d, ws.pos[e], g.pts);
+          }
+          __syncwarp();
+        }
+        // merge the 32 private lists: K rounds of "smallest head wins"
+#pragma unroll
+        for (int rr = 0; rr < TK::kK; rr++) {
+          float gd = part.d[0];
+          int gp = part.p[0];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(FULL, gd, off);
+            const int op = __shfl_xor_sync(FULL, gp, off);
+            if (TK::before(od, op, gd, gp, g.pts)) { gd = od; gp = op; }
+          }
+          if (gp >= 0 && gp == part.p[0]) part.pop_front();
+          if (lane == mi) best.append_shift(gd, gp);   // K appends leave the list in ascending order
+        }
+      }
+    } else {
+      int r = 0;
+      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
+        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
+        r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+        if (member) {
+#pragma unroll 4
+          for (int e = 0; e < nch; e++) {
+            const float4 p = ws.pts[e];
+            const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
+            if (d <= best.worst()) best.offer(d, ws.pos[e], g.pts);
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- 5. termination test of the members (same bound as grid_knn, faces of the 4x4x4 block)
+    if (member) {
+      const float hL = h0 * (float)(1 << Lg);
+      float gap = __int_as_float(0x7f800000);
+      {
+        const int lo_c = 2 * lpx - 1, hi_c = 2 * lpx + 2;
+        if (lo_c > 0) gap = fminf(gap, fmaxf(ux - (float)lo_c * hL, 0.0f));
+        if (hi_c < maxc) gap = fminf(gap, fmaxf((float)(hi_c + 1) * hL - ux, 0.0f));
+      }
+      {
+        const int lo_c = 2 * lpy - 1, hi_c = 2 * lpy + 2;
+        if (lo_c > 0) gap = fminf(gap, fmaxf(uy - (float)lo_c * hL, 0.0f));
+        if (hi_c < maxc) gap = fminf(gap, fmaxf((float)(hi_c + 1) * hL - uy, 0.0f));
+      }
+      {
+        const int lo_c = 2 * lpz - 1, hi_c = 2 * lpz + 2;
+        if (lo_c > 0) gap = fminf(gap, fmaxf(uz - (float)lo_c * hL, 0.0f));
+        if (hi_c < maxc) gap = fminf(gap, fmaxf((float)(hi_c + 1) * hL - uz, 0.0f));
+      }
+      const float covered = fmaxf(gap - margin, 0.0f);
+      const float cov2 = covered * covered * 0.999999f;
+      if (Lg >= kTopLevel || best.worst() < cov2 || cov2 >= max_sqd) done = true;
+      else Lmin = Lg + 1;
+    }
+    WKNN_STAT(4, __popc(__ballot_sync(FULL, member && !done)));
+  }
+}
+
+}  // namespace ngicp
