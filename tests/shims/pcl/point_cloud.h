@@ -1,0 +1,14 @@
+// TEST-ONLY shim of pcl::PointCloud<PointT> (PCL is absent from this image). Not shipped.
+#pragma once
+#include <memory>
+#include <vector>
+namespace pcl {
+template <typename PointT>
+struct PointCloud {
+  using Ptr = std::shared_ptr<PointCloud<PointT>>;
+  using ConstPtr = std::shared_ptr<const PointCloud<PointT>>;
+  std::vector<PointT> points;
+  size_t size() const { return points.size(); }
+  const PointT& at(size_t i) const { return points.at(i); }
+};
+}  // namespace pcl
