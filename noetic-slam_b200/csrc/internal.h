@@ -73,6 +73,8 @@ struct ngicp_handle {
   // tuning knobs (env NGICP_K4_CMAX / NGICP_K2_CMAX_MULT override)
   int k4_cmax = 64;
   int k2_cmax_mult = 4;
+  int k2_lpq = 0;   // lanes per query in K2 (0 = pick by cloud size)
+  int k4_lpq = 0;
   // LM state (lsq_registration.h:151-168)
   double lm_lambda = -1.0;
   double final_hessian[36];

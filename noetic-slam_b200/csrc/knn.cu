@@ -44,20 +44,21 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
   }
 }
 
-// Production K2: one warp per 32 consecutive (Morton-sorted) points, shared staged candidates (wknn.cuh).
+// Production K2: a warp owns 32/LPQ consecutive (Morton-sorted) points, LPQ lanes per point, shared staged
+// candidates (wknn.cuh).
 constexpr int kSelfWarps = 4;
-template <int K>
-__global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int start_count, int normalization,
+template <int K, int LPQ>
+__global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int cmax, int normalization,
                                                                         int* __restrict__ nbr, double* __restrict__ dens_term) {
   __shared__ WarpScratch scratch[kSelfWarps];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.x * (blockDim.x / LPQ) + threadIdx.x / LPQ;
   const bool active = j < g.n;
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   int seg = 0;
   if (active) { q = __ldg(g.pts + j); seg = find_segment(g.seg_start, g.n_seg, j); }
   TopK<K> best;
-  warp_knn(g, active, q.x, q.y, q.z, seg, k, start_count, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5]);
-  if (!active) return;
+  warp_knn<LPQ>(g, active, q.x, q.y, q.z, seg, k, cmax, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5]);
+  if (!active || (threadIdx.x & (LPQ - 1)) != 0) return;
   int* row = nbr + (size_t)j * k;
   if (k == K && (K % 4) == 0) {
 #pragma unroll
@@ -149,7 +150,12 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   const int normalization = ((k - 1) * (2 + k)) / 2;  // integer arithmetic, nano_gicp.cc:345
   const int sc = start_count_for(k);
   cudaStream_t s = h->stream;
-#define LAUNCH_SELF(K) knn_self_warp_kernel<K><<<(n + 32 * kSelfWarps - 1) / (32 * kSelfWarps), 32 * kSelfWarps, 0, s>>>(g, k, group_cap_for(k, h->k2_cmax_mult), normalization, d_nbr, d_dens_term)
+  // lanes per query: small clouds need the extra warps, big ones prefer the sharing of one query per lane
+  const int lpq = h->k2_lpq > 0 ? h->k2_lpq : (n < 1500000 ? 4 : 1);
+#define LAUNCH_SELF_L(K, LPQ)                                                                                             \
+  knn_self_warp_kernel<K, LPQ><<<(n + (32 * kSelfWarps / LPQ) - 1) / (32 * kSelfWarps / LPQ), 32 * kSelfWarps, 0, s>>>( \
+      g, k, group_cap_for(k, h->k2_cmax_mult), normalization, d_nbr, d_dens_term)
+#define LAUNCH_SELF(K) do { if (lpq >= 4) LAUNCH_SELF_L(K, 4); else LAUNCH_SELF_L(K, 1); } while (0)
   if (k == 1) LAUNCH_SELF(1);
   else if (k <= 8) LAUNCH_SELF(8);
   else if (k <= 16) LAUNCH_SELF(16);
@@ -157,6 +163,7 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   else if (k <= 32) LAUNCH_SELF(32);
   else knn_self_dyn_kernel<kMaxK><<<(n + 63) / 64, 64, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term);
 #undef LAUNCH_SELF
+#undef LAUNCH_SELF_L
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;

@@ -83,19 +83,12 @@ __device__ __forceinline__ void cross3(const double a[3], double bx, double by, 
 // Reduce `NT` per-thread doubles over the block, publish the block partial, and let the last
 // block of this batch entry (blockIdx.y) fold all partials (Neumaier) into the result slot.
 template <int NT>
-__device__ __forceinline__ void block_reduce_and_publish(double acc[NT], double* __restrict__ partials, unsigned int* __restrict__ counters,
-                                                         ReduceSlot* __restrict__ slots, unsigned long long seq) {
+__device__ __forceinline__ void block_publish(double (*sm)[NT], double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                              ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  // sm[warp][term] holds every warp's running sums (written by that warp's lane 0)
   constexpr int kWarps = kLinThreads / 32;
-  __shared__ double sm[kWarps][NT];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int t = 0; t < NT; t++) {
-    double v = acc[t];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) sm[warp][t] = v;
-  }
   __syncthreads();
   const int b = blockIdx.y;
   double* my = partials + ((size_t)b * gridDim.x + blockIdx.x) * 32;
@@ -144,7 +137,7 @@ __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* _
 
 // K4. grid = (blocks per scan, scans). Source scan b = source segment b; its target segment is
 // target_seg[b] (or 0).
-template <bool WANT_HB>
+template <bool WANT_HB, int LPQ>
 __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
                                                                  PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ target_seg,
                                                                  double thr2, float max_sqd, int cmax, int* __restrict__ corr,
@@ -155,15 +148,15 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
   const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
   const int tseg = target_seg ? __ldg(target_seg + b) : 0;
-  double acc[kTerms];
-#pragma unroll
-  for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
-
   __shared__ WarpScratch scratch[kLinThreads / 32];
+  __shared__ double wsum[kLinThreads / 32][kTerms];   // per-warp running sums: keeps 58 registers free during the search
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < kTerms) wsum[warp][lane] = 0.0;
+  __syncwarp();
   // warp-uniform trip count: the whole warp runs the cooperative search together (wknn.cuh)
-  for (int j0 = begin + blockIdx.x * kLinThreads + warp * 32; j0 < end; j0 += gridDim.x * kLinThreads) {
-    const int j = j0 + lane;
+  // LPQ lanes share one source point during the search; lane 0 of the group does the point's arithmetic
+  for (int j0 = begin + (blockIdx.x * kLinThreads + warp * 32) / LPQ; j0 < end; j0 += gridDim.x * kLinThreads / LPQ) {
+    const int j = j0 + lane / LPQ;
     const bool active = j < end;
     const float4 pa = active ? __ldg(src.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     // fp32 transform of the query, ((r0*x + r1*y) + r2*z) + t*w with w = 1 (nano_gicp.cc:222)
@@ -172,11 +165,15 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
     for (int r = 0; r < 3; r++)
       qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
     TopK<1> best;
-    warp_knn(tgt, active, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
+    warp_knn<LPQ>(tgt, active, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
     const int pos = best.p[0];
-    const bool valid = active && pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
-    if (active) corr[j] = valid ? pos : -1;
-    if (!valid) continue;
+    const bool owner = active && (lane & (LPQ - 1)) == 0;
+    const bool valid = owner && pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
+    if (owner) corr[j] = valid ? pos : -1;
+    double acc[kTerms];
+#pragma unroll
+    for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
+    if (valid) {
     const float4 pb = __ldg(tgt.pts + pos);
     float ca[6], cb[6];
     {
@@ -217,8 +214,19 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
       acc[21] -= qm[0]; acc[22] -= qm[1]; acc[23] -= qm[2];
       acc[24] -= Me[0]; acc[25] -= Me[1]; acc[26] -= Me[2];
     }
+    }
+    // only the owner lanes (every LPQ-th) carry values: reduce across them, lane 0 banks the warp's sum
+    if (__any_sync(0xffffffffu, valid)) {
+#pragma unroll
+      for (int t = 0; t < kTerms; t++) {
+        double v = acc[t];
+#pragma unroll
+        for (int off = 16; off >= LPQ; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) wsum[warp][t] += v;
+      }
+    }
   }
-  block_reduce_and_publish<kTerms>(acc, partials, counters, slots, seq);
+  block_publish<kTerms>(wsum, partials, counters, slots, seq);
 }
 
 // K5. Trial pose P, Mahalanobis rebuilt at the linearisation pose P0.
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(kLinThreads) error_kernel(GridView src, GridVi
   const int b = blockIdx.y;
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
   const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
+  __shared__ double wsum[kLinThreads / 32][1];
   double acc[1] = {0.0};
   for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
     const int pos = __ldg(corr + j);
@@ -250,7 +259,13 @@ __global__ void __launch_bounds__(kLinThreads) error_kernel(GridView src, GridVi
     residual(P, pa, pb, q, e);
     acc[0] += quad_form(M, e, Me);
   }
-  block_reduce_and_publish<1>(acc, partials, counters, slots, seq);
+  {
+    double v = acc[0];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][0] = v;
+  }
+  block_publish<1>(wsum, partials, counters, slots, seq);
 }
 
 // API-parity export of update_correspondences in ORIGINAL source order (slow path, tests only)
@@ -318,7 +333,7 @@ static float max_sqd_for(double thr) {
 }
 
 int lin_blocks_for(int n) {
-  const int want = (n + kLinThreads - 1) / kLinThreads;  // one point per thread: the search is latency-bound, spread it wide
+  const int want = (n + kLinThreads - 1) / kLinThreads;  // one search lane-group per thread slot: latency-bound, spread it wide
   return std::max(1, std::min(want, kMaxLinBlocks));
 }
 
@@ -367,15 +382,16 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
   const PoseArg P = make_pose(T);
   const double thr = h->params.max_corr_dist;
   const double thr2 = thr * thr;
-  const dim3 grid(lin_blocks_for(si->n), 1);
+  const int lpq = h->k4_lpq > 0 ? h->k4_lpq : 4;
+  const dim3 grid(lin_blocks_for(si->n * (lpq >= 4 ? 4 : 1)), 1);
   const unsigned long long seq = ++h->seq;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-  if (want_Hb)
-    linearize_kernel<true><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
-                                                              max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq);
-  else
-    linearize_kernel<false><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, thr2,
-                                                               max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq);
+#define LAUNCH_LIN(HB, LPQ)                                                                                                              \
+  linearize_kernel<HB, LPQ><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, \
+                                                                 thr2, max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq)
+  if (want_Hb) { if (lpq >= 4) LAUNCH_LIN(true, 4); else LAUNCH_LIN(true, 1); }
+  else { if (lpq >= 4) LAUNCH_LIN(false, 4); else LAUNCH_LIN(false, 1); }
+#undef LAUNCH_LIN
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);

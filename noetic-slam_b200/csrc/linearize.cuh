@@ -6,7 +6,7 @@
 
 namespace ngicp {
 
-constexpr int kMaxLinBlocks = 148 * 8;
+constexpr int kMaxLinBlocks = 148 * 16;
 constexpr int kMaxBatch = 256;
 
 // Pose handed to the kernels by value: fp64 for the residual / Mahalanobis, fp32 for the

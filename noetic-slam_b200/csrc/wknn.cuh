@@ -21,7 +21,7 @@
 
 namespace ngicp {
 
-constexpr int kWarpChunk = 128;  // candidates staged per pass and warp
+constexpr int kWarpChunk = 256;  // candidates staged per pass and warp
 
 #ifdef NGICP_STATS
 // development counters: [0] passes, [1] staged candidates, [2] member lanes, [3] warp_knn calls, [4] refused members
@@ -31,13 +31,34 @@ static __device__ unsigned long long g_wknn_stats[8];
 #define WKNN_STAT(i, v) do { } while (0)
 #endif
 
-struct WarpScratch {
-  float4 pts[kWarpChunk];
-  int pos[kWarpChunk];
-  uint32_t rstart[64];
-  uint32_t rpre[65];
-  uint32_t pad[3];
+struct __align__(16) WarpScratch {
+  float4 pts[kWarpChunk];       // staged candidates (written by the TMA bulk copies)
+  int pos[kWarpChunk];          // their sorted positions
+  uint32_t rstart[64];          // non-empty voxel buckets of the block, compacted, in scan order
+  uint32_t rpre[65];            // exclusive prefix of their sizes; rpre[R] = M
+  uint32_t pad;
+  unsigned long long mbar;      // mbarrier the bulk copies complete on (one per warp)
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
 
 // block cells in scan order: the 8 children of the group cell first (they hold the nearest candidates,
 // so the top-k threshold tightens early and later candidates rarely insert), then the surrounding ring.
@@ -49,24 +70,43 @@ __device__ __constant__ unsigned char kBlockOrder[64] = {
     0x20, 0x21, 0x22, 0x23, 0x24, 0x27, 0x28, 0x2b, 0x2c, 0x2d, 0x2e, 0x2f,
     0x30, 0x31, 0x32, 0x33, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x3b, 0x3c, 0x3d, 0x3e, 0x3f};
 
-// copy candidates [c0, c0+nch) of the concatenated bucket list into shared memory; returns the range cursor
-__device__ __forceinline__ int wknn_stage_chunk(const GridView& g, WarpScratch& ws, int lane, uint32_t c0, int nch, int r) {
-  for (int e = lane; e < nch; e += 32) {
-    const uint32_t ge = c0 + e;
-    while (ws.rpre[r + 1] <= ge) r++;
-    const int gp = (int)(ws.rstart[r] + (ge - ws.rpre[r]));
-    ws.pts[e] = __ldg(g.pts + gp);
-    ws.pos[e] = gp;
+// Stage candidates [c0, c0+nch) of the concatenated bucket list into shared memory. Every voxel bucket is a
+// contiguous run of float4 in the Morton-sorted array, so each overlapping bucket is ONE TMA bulk copy
+// (cp.async.bulk, issued by the lane that owns the bucket); while the copies are in flight the warp fills in
+// the candidates' sorted positions with plain shared stores, then waits on the mbarrier.
+__device__ __forceinline__ void wknn_stage_chunk(const GridView& g, WarpScratch& ws, int lane, int R, uint32_t c0, int nch, uint32_t& phase) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the previous chunk before async writes
+  if (lane == 0) mbar_expect_tx(&ws.mbar, (uint32_t)nch * 16u);
+  const uint32_t c1 = c0 + (uint32_t)nch;
+  for (int ri = lane; ri < R; ri += 32) {
+    const uint32_t pre = ws.rpre[ri], nxt = ws.rpre[ri + 1];
+    const uint32_t lo = max(pre, c0), hi = min(nxt, c1);
+    if (lo < hi) tma_bulk_g2s(&ws.pts[lo - c0], g.pts + (ws.rstart[ri] + (lo - pre)), (hi - lo) * 16u, &ws.mbar);
   }
+  for (int ri = 0; ri < R; ri++) {
+    const uint32_t pre = ws.rpre[ri], nxt = ws.rpre[ri + 1];
+    if (nxt <= c0) continue;
+    if (pre >= c1) break;
+    const uint32_t lo = max(pre, c0), hi = min(nxt, c1), s = ws.rstart[ri];
+    for (uint32_t ge = lo + lane; ge < hi; ge += 32) ws.pos[ge - c0] = (int)(s + (ge - pre));
+  }
+  unsigned int spins = 0;
+  while (!mbar_try_wait(&ws.mbar, phase)) {
+    if (++spins > (1u << 24)) __trap();   // never hang the GPU on a programming error
+  }
+  phase ^= 1u;
   __syncwarp();
-  return r;
 }
 
-template <class TK>
+// LPQ = lanes per query (1, 2, 4 or 8). The LPQ lanes of a query hold identical query state and split the
+// staged candidates between them, which multiplies the number of warps a small cloud can keep in flight
+// (a 65,536-point scan is only 2,048 warps at one query per lane) and shortens every warp's dependent chain.
+template <int LPQ, class TK>
 __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float qx, float qy, float qz, int seg, int k, int cmax,
                                          float max_sqd, TK& best, WarpScratch& ws) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPQ - 1);
   const GridMeta* __restrict__ m = g.meta;
   const float h0 = __ldg(&m->h0), inv_h0 = __ldg(&m->inv_h0), margin = __ldg(&m->margin);
   const int base = __ldg(&m->base_level);
@@ -84,6 +124,9 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     if (reach * reach * 0.999999f >= max_sqd) break;
   }
 
+  if (lane == 0) mbar_init(&ws.mbar, 1);
+  __syncwarp();
+  uint32_t phase = 0;   // parity of the mbarrier phase the next staged chunk completes
   int Lmin = base;  // finest group level this lane still accepts
   bool done = !active;
   best.reset();
@@ -127,7 +170,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
 
     // ---- 3. 64 hash probes, two per lane; ranges + exclusive prefix of their sizes into shared memory
     const unsigned long long sgL = sgbits >> (3 * Lg);
-    uint32_t cnt[2];
+    uint32_t cnt[2], st[2];
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       const int ci = lane + 32 * half;
@@ -138,7 +181,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
         const unsigned long long ck = ((sgL | morton3((unsigned)ax, (unsigned)ay, (unsigned)az)) << 4) | (unsigned)Lg;
         if (!cell_lookup(g.table, g.table_mask, ck, s, e)) { s = 0; e = 0; }
       }
-      ws.rstart[ci] = s;
+      st[half] = s;
       cnt[half] = e - s;
     }
     uint32_t inc0 = cnt[0], inc1 = cnt[1];
@@ -149,9 +192,13 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     }
     const uint32_t tot0 = __shfl_sync(FULL, inc0, 31);
     const uint32_t M = tot0 + __shfl_sync(FULL, inc1, 31);
-    ws.rpre[lane] = inc0 - cnt[0];
-    ws.rpre[lane + 32] = tot0 + inc1 - cnt[1];
-    if (lane == 0) ws.rpre[64] = M;
+    // keep only the non-empty buckets, in scan order
+    const unsigned nz0 = __ballot_sync(FULL, cnt[0] != 0), nz1 = __ballot_sync(FULL, cnt[1] != 0);
+    const unsigned lt = (1u << lane) - 1u;
+    const int R = __popc(nz0) + __popc(nz1);
+    if (cnt[0]) { const int i0 = __popc(nz0 & lt); ws.rstart[i0] = st[0]; ws.rpre[i0] = inc0 - cnt[0]; }
+    if (cnt[1]) { const int i1 = __popc(nz0) + __popc(nz1 & lt); ws.rstart[i1] = st[1]; ws.rpre[i1] = tot0 + inc1 - cnt[1]; }
+    if (lane == 0) ws.rpre[R] = M;
     __syncwarp();
     if (member) best.reset();
     WKNN_STAT(0, 1); WKNN_STAT(1, M); WKNN_STAT(2, __popc(__ballot_sync(FULL, member)));
@@ -165,19 +212,19 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     //   split, k>1  : per member, the lanes split all candidates into private top-k lists that are merged by
     //                 K rounds of warp-argmin; pays off for the heavy tail (few members, thousands of candidates)
     const unsigned mem_mask = __ballot_sync(FULL, member);
-    const int nmem = __popc(mem_mask);
+    const int nmem = __popc(mem_mask) / LPQ;
+    const unsigned grp_mask = (LPQ == 32 ? 0xffffffffu : ((1u << LPQ) - 1u));
     if (TK::kK == 1) {
-      int r = 0;
       for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
         const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-        r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
         float4 cand[kWarpChunk / 32];
 #pragma unroll
         for (int t = 0; t < kWarpChunk / 32; t++) cand[t] = ws.pts[min(lane + 32 * t, nch - 1)];
         unsigned rem = mem_mask;
         while (rem) {
-          const int mi = __ffs(rem) - 1;
-          rem &= rem - 1;
+          const int mi = __ffs(rem) - 1;                 // first lane of the next member query
+          rem &= ~(grp_mask << (mi & ~(LPQ - 1)));
           const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
           float bd = __int_as_float(0x7f800000);
           int be = -1;
@@ -194,22 +241,22 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
             const int op = __shfl_xor_sync(FULL, bp, off);
             if (TK::before(od, op, bd, bp, g.pts)) { bd = od; bp = op; }
           }
-          if (lane == mi && bp >= 0 && bd <= best.worst()) best.offer(bd, bp, g.pts);
+          if ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1)) && bp >= 0 && bd <= best.worst()) best.offer(bd, bp, g.pts);
         }
         __syncwarp();
       }
-    } else if ((long long)nmem * (3ll * M + 1000) < 60ll * M) {
+    } else if ((long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M) {
+      // heavy tail: few member queries, many candidates -> all 32 lanes split the candidates of one query
       unsigned rem = mem_mask;
       while (rem) {
         const int mi = __ffs(rem) - 1;
-        rem &= rem - 1;
+        rem &= ~(grp_mask << (mi & ~(LPQ - 1)));
         const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
         TK part;
         part.reset();
-        int r = 0;
         for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
           const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-          r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+          wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
           for (int e = lane; e < nch; e += 32) {
             const float4 p = ws.pts[e];
             const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
@@ -217,9 +264,9 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           }
           __syncwarp();
         }
-        // merge the 32 private lists: K rounds of "smallest head wins"
+        const bool mine = (lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1));
 #pragma unroll
-        for (int rr = 0; rr < TK::kK; rr++) {
+        for (int rr = 0; rr < TK::kK; rr++) {   // merge the 32 private lists: K rounds of "smallest head wins"
           float gd = part.d[0];
           int gp = part.p[0];
 #pragma unroll
@@ -229,14 +276,13 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
             if (TK::before(od, op, gd, gp, g.pts)) { gd = od; gp = op; }
           }
           if (gp >= 0 && gp == part.p[0]) part.pop_front();
-          if (lane == mi) best.append_shift(gd, gp);   // K appends leave the list in ascending order
+          if (mine) best.append_shift(gd, gp);   // K appends leave the list in ascending order
         }
       }
-    } else {
-      int r = 0;
+    } else if (LPQ == 1) {
       for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
         const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-        r = wknn_stage_chunk(g, ws, lane, c0, nch, r);
+        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
         if (member) {
 #pragma unroll 4
           for (int e = 0; e < nch; e++) {
@@ -246,6 +292,37 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           }
         }
         __syncwarp();
+      }
+    } else {
+      // shared mode, LPQ lanes per query: lane `sub` takes candidates sub, sub+LPQ, ... into a private list,
+      // then the LPQ lists of a query are merged by K rounds of group-argmin (xor shuffles inside the group)
+      TK part;
+      part.reset();
+      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
+        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
+        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
+        if (member) {
+#pragma unroll 2
+          for (int e = sub; e < nch; e += LPQ) {
+            const float4 p = ws.pts[e];
+            const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
+            if (d <= part.worst()) part.offer(d, ws.pos[e], g.pts);
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int rr = 0; rr < TK::kK; rr++) {
+        float gd = part.d[0];
+        int gp = part.p[0];
+#pragma unroll
+        for (int off = LPQ / 2; off > 0; off >>= 1) {
+          const float od = __shfl_xor_sync(FULL, gd, off);
+          const int op = __shfl_xor_sync(FULL, gp, off);
+          if (TK::before(od, op, gd, gp, g.pts)) { gd = od; gp = op; }
+        }
+        if (gp >= 0 && gp == part.p[0]) part.pop_front();
+        if (member) best.append_shift(gd, gp);
       }
     }
 
