@@ -42,7 +42,8 @@ struct GridMeta {
 
 // Read-only view handed to the kernels by value.
 struct GridView {
-  const float4* pts;        // [n] sorted
+  const float4* pts;        // [n] sorted, .w = original index
+  const int* inv;           // [n] original index -> sorted position
   const CellSlot* table;    // [table_mask+1]
   const GridMeta* meta;
   const float4* seg_origin; // [n_seg] lower bbox corner of each segment (keyframe)
@@ -116,9 +117,11 @@ __device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float 
 }
 
 // ------------------------------------------------------------------------------------ top-K
-// Register-resident sorted list of the K best (distance, sorted-position) pairs, ascending by
-// (distance, ORIGINAL index). Positions are what the kernels gather with; the original index
-// (pts[pos].w) is only fetched to break exact distance ties.
+// Register-resident sorted list of the K best (distance, ORIGINAL index) pairs, ascending by
+// (distance, index) — the documented tie-break. The original index rides in the .w lane of every
+// staged point, so ties are broken in registers; kernels that need sorted positions translate
+// through the index's inverse permutation when they write their results. Empty slots hold
+// (+inf, -1); indices compare as unsigned so -1 sorts last.
 template <int K>
 struct TopK {
   static constexpr int kK = K;
@@ -139,32 +142,28 @@ struct TopK {
 #pragma unroll
     for (int i = 0; i < K; i++) { d[i] = __int_as_float(0x7f800000); p[i] = -1; }
   }
-  __device__ __forceinline__ static bool before(float da, int pa, float db, int pb, const float4* __restrict__ pts) {
-    if (da < db) return true;
-    if (da > db) return false;
-    if (pb < 0) return pa >= 0;
-    if (pa < 0) return false;
-    return __float_as_int(__ldg(&pts[pa].w)) < __float_as_int(__ldg(&pts[pb].w));
+  __device__ __forceinline__ static bool before(float da, int pa, float db, int pb) {
+    return da < db || (da == db && (unsigned)pa < (unsigned)pb);
   }
   // slow path: full (distance, original index) ordering, only taken when a distance is exactly tied
-  __device__ __forceinline__ void offer_tied(float dn, int pn, const float4* __restrict__ pts) {
-    if (!before(dn, pn, d[K - 1], p[K - 1], pts)) return;
+  __device__ __forceinline__ void offer_tied(float dn, int pn) {
+    if (!before(dn, pn, d[K - 1], p[K - 1])) return;
     d[K - 1] = dn; p[K - 1] = pn;
 #pragma unroll
     for (int i = K - 1; i > 0; i--) {
-      if (before(d[i], p[i], d[i - 1], p[i - 1], pts)) {
+      if (before(d[i], p[i], d[i - 1], p[i - 1])) {
         const float td = d[i]; d[i] = d[i - 1]; d[i - 1] = td;
         const int tp = p[i]; p[i] = p[i - 1]; p[i - 1] = tp;
       }
     }
   }
   // fast path: rank-and-shift with independent selects (no dependent compare-swap chain)
-  __device__ __forceinline__ void offer(float dn, int pn, const float4* __restrict__ pts) {
+  __device__ __forceinline__ void offer(float dn, int pn) {
     if (dn > d[K - 1]) return;
     bool tie = false;
 #pragma unroll
     for (int i = 0; i < K; i++) tie |= (d[i] == dn);
-    if (tie) { offer_tied(dn, pn, pts); return; }
+    if (tie) { offer_tied(dn, pn); return; }
 #pragma unroll
     for (int i = K - 1; i > 0; i--) {
       const bool lti = d[i] < dn, ltm = d[i - 1] < dn;
@@ -194,11 +193,11 @@ struct TopKDyn {
   __device__ __forceinline__ void reset() {
     for (int i = 0; i < cap; i++) { d[i] = __int_as_float(0x7f800000); p[i] = -1; }
   }
-  __device__ __forceinline__ void offer(float dn, int pn, const float4* __restrict__ pts) {
+  __device__ __forceinline__ void offer(float dn, int pn) {
     if (dn > d[cap - 1]) return;
-    if (!TopK<1>::before(dn, pn, d[cap - 1], p[cap - 1], pts)) return;
+    if (!TopK<1>::before(dn, pn, d[cap - 1], p[cap - 1])) return;
     int i = cap - 1;
-    while (i > 0 && TopK<1>::before(dn, pn, d[i - 1], p[i - 1], pts)) { d[i] = d[i - 1]; p[i] = p[i - 1]; i--; }
+    while (i > 0 && TopK<1>::before(dn, pn, d[i - 1], p[i - 1])) { d[i] = d[i - 1]; p[i] = p[i - 1]; i--; }
     d[i] = dn; p[i] = pn;
   }
   __device__ __forceinline__ float worst() const { return d[cap - 1]; }
@@ -261,7 +260,7 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
           if (!cell_lookup(g.table, g.table_mask, ck, s, e)) continue;
           for (uint32_t j = s; j < e; j++) {
             const float4 p = __ldg(g.pts + j);
-            best.offer(sqdist_ref(qx, qy, qz, p.x, p.y, p.z), (int)j, g.pts);
+            best.offer(sqdist_ref(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
           }
         }
       }

@@ -111,12 +111,13 @@ __global__ void __launch_bounds__(256) keys_kernel(const float* __restrict__ xyz
 }
 
 __global__ void __launch_bounds__(256) gather_points_kernel(const float* __restrict__ xyz, int stride, int n, const uint32_t* __restrict__ vals,
-                                                            float4* __restrict__ pts) {
+                                                            float4* __restrict__ pts, int* __restrict__ inv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint32_t i = vals[j];
   const float* p = xyz + (size_t)i * stride;
   pts[j] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
+  inv[i] = j;
 }
 
 // first level at which two keys fall into different cells, +1; kNumLevels (13) if they differ at the top
@@ -205,6 +206,7 @@ inline int ceil_log2(unsigned int v) { int b = 0; while ((1u << b) < v) b++; ret
 void free_index(Index* idx, cudaStream_t stream) {
   if (!idx) return;
   dev_free(idx->pts, stream);
+  dev_free(idx->inv, stream);
   dev_free(idx->keys, stream);
   dev_free(idx->table, stream);
   dev_free(idx->meta, stream);
@@ -255,6 +257,7 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   } while (0)
 
   IDX_CUDA(dev_alloc(&idx->pts, (size_t)n, s));
+  IDX_CUDA(dev_alloc(&idx->inv, (size_t)n, s));
   IDX_CUDA(dev_alloc(&idx->table, (size_t)cap, s));
   IDX_CUDA(dev_alloc(&idx->meta, 1, s));
   IDX_CUDA(dev_alloc(&idx->seg_origin, (size_t)n_seg, s));
@@ -283,7 +286,7 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   keys_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, idx->seg_origin, idx->meta, keys_a, vals_a);
   count_launch(h, 4);
   count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, nbits, s, &keys_sorted, &vals_sorted));
-  gather_points_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, idx->pts);
+  gather_points_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, idx->pts, idx->inv);
   level_hist_kernel<<<std::min(nb, 148 * 8), tpb, 0, s>>>(keys_sorted, n, idx->meta);
   choose_base_kernel<<<1, 32, 0, s>>>(idx->meta, n, cap / 2, 2);
   table_insert_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask);

@@ -33,6 +33,7 @@ struct ngicp_index {
   int n = 0;
   int n_seg = 1;
   float4* pts = nullptr;                  // [n] Morton-sorted, .w = original index
+  int* inv = nullptr;                     // [n] original index -> sorted position
   unsigned long long* keys = nullptr;     // [n] sorted voxel keys
   ngicp::CellSlot* table = nullptr;
   uint32_t table_mask = 0;
@@ -42,7 +43,7 @@ struct ngicp_index {
   std::vector<int64_t> seg_offsets_host;  // [n_seg+1]
   ngicp::GridView view() const {
     ngicp::GridView g;
-    g.pts = pts; g.table = table; g.meta = meta; g.seg_origin = seg_origin; g.seg_start = seg_start;
+    g.pts = pts; g.inv = inv; g.table = table; g.meta = meta; g.seg_origin = seg_origin; g.seg_start = seg_start;
     g.table_mask = table_mask; g.n = n; g.n_seg = n_seg;
     return g;
   }

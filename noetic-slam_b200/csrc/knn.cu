@@ -12,6 +12,9 @@ namespace ngicp {
 
 namespace {
 
+// original index -> sorted position (what K3 gathers with); -1 stays -1
+__device__ __forceinline__ int topos(const GridView& g, int orig) { return orig >= 0 ? __ldg(g.inv + orig) : -1; }
+
 template <class TK>
 __device__ __forceinline__ void self_query(const GridView& g, int j, int k, int start_count, int normalization,
                                            int* __restrict__ nbr, double* __restrict__ dens_term, TK& best) {
@@ -30,10 +33,11 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
   int* row = nbr + (size_t)j * k;
   if (k == K && (K % 4) == 0) {
 #pragma unroll
-    for (int i = 0; i < K; i += 4) reinterpret_cast<int4*>(row)[i / 4] = make_int4(best.p[i], best.p[i + 1], best.p[i + 2], best.p[i + 3]);
+    for (int i = 0; i < K; i += 4)
+      reinterpret_cast<int4*>(row)[i / 4] = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
   } else {
 #pragma unroll
-    for (int i = 0; i < K; i++) if (i < k) row[i] = best.p[i];
+    for (int i = 0; i < K; i++) if (i < k) row[i] = topos(g, best.p[i]);
   }
   if (dens_term) {
     // nano_gicp.cc:345-346: accumulate(k_sq_distances.begin()+1, end, 0.0) / normalization
@@ -62,10 +66,11 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
   int* row = nbr + (size_t)j * k;
   if (k == K && (K % 4) == 0) {
 #pragma unroll
-    for (int i = 0; i < K; i += 4) reinterpret_cast<int4*>(row)[i / 4] = make_int4(best.p[i], best.p[i + 1], best.p[i + 2], best.p[i + 3]);
+    for (int i = 0; i < K; i += 4)
+      reinterpret_cast<int4*>(row)[i / 4] = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
   } else {
 #pragma unroll
-    for (int i = 0; i < K; i++) if (i < k) row[i] = best.p[i];
+    for (int i = 0; i < K; i++) if (i < k) row[i] = topos(g, best.p[i]);
   }
   if (dens_term) {
     double acc = 0.0;
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(64) knn_self_dyn_kernel(GridView g, int k, int
   best.cap = k;
   self_query(g, j, k, start_count, normalization, nbr, dens_term, best);
   int* row = nbr + (size_t)j * k;
-  for (int i = 0; i < k; i++) row[i] = best.p[i];
+  for (int i = 0; i < k; i++) row[i] = topos(g, best.p[i]);
   if (dens_term) {
     double acc = 0.0;
     for (int i = 1; i < k; i++) acc += (double)best.d[i];
@@ -97,7 +102,7 @@ __device__ __forceinline__ void write_public(const GridView& g, const TK& best, 
   for (int i = 0; i < k; i++) {
     int p = -1; float d = __int_as_float(0x7f800000);
     if (i < cap) { p = best.p[i]; d = best.d[i]; }
-    oi[i] = p >= 0 ? __float_as_int(__ldg(&g.pts[p].w)) : -1;
+    oi[i] = p;
     od[i] = p >= 0 ? d : __int_as_float(0x7f800000);
   }
 }
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(128) knn_query_kernel(GridView g, const float4
   for (int t = 0; t < K; t++) {
     if (t < k) {
       const int p = best.p[t];
-      oi[t] = p >= 0 ? __float_as_int(__ldg(&g.pts[p].w)) : -1;
+      oi[t] = p;
       od[t] = p >= 0 ? best.d[t] : __int_as_float(0x7f800000);
     }
   }

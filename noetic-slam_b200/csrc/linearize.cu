@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
       qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
     TopK<1> best;
     warp_knn<LPQ>(tgt, active, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
-    const int pos = best.p[0];
+    const int pos = best.p[0] >= 0 ? __ldg(tgt.inv + best.p[0]) : -1;   // original index -> sorted position
     const bool owner = active && (lane & (LPQ - 1)) == 0;
     const bool valid = owner && pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
     if (owner) corr[j] = valid ? pos : -1;

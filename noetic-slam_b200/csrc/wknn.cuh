@@ -33,7 +33,6 @@ static __device__ unsigned long long g_wknn_stats[8];
 
 struct __align__(16) WarpScratch {
   float4 pts[kWarpChunk];       // staged candidates (written by the TMA bulk copies)
-  int pos[kWarpChunk];          // their sorted positions
   uint32_t rstart[64];          // non-empty voxel buckets of the block, compacted, in scan order
   uint32_t rpre[65];            // exclusive prefix of their sizes; rpre[R] = M
   uint32_t pad;
@@ -72,8 +71,8 @@ __device__ __constant__ unsigned char kBlockOrder[64] = {
 
 // Stage candidates [c0, c0+nch) of the concatenated bucket list into shared memory. Every voxel bucket is a
 // contiguous run of float4 in the Morton-sorted array, so each overlapping bucket is ONE TMA bulk copy
-// (cp.async.bulk, issued by the lane that owns the bucket); while the copies are in flight the warp fills in
-// the candidates' sorted positions with plain shared stores, then waits on the mbarrier.
+// (cp.async.bulk, issued by the lane that owns the bucket), then the warp waits on the mbarrier. The original
+// index of every candidate rides in the .w lane of the copied float4.
 __device__ __forceinline__ void wknn_stage_chunk(const GridView& g, WarpScratch& ws, int lane, int R, uint32_t c0, int nch, uint32_t& phase) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the previous chunk before async writes
   if (lane == 0) mbar_expect_tx(&ws.mbar, (uint32_t)nch * 16u);
@@ -82,13 +81,6 @@ __device__ __forceinline__ void wknn_stage_chunk(const GridView& g, WarpScratch&
     const uint32_t pre = ws.rpre[ri], nxt = ws.rpre[ri + 1];
     const uint32_t lo = max(pre, c0), hi = min(nxt, c1);
     if (lo < hi) tma_bulk_g2s(&ws.pts[lo - c0], g.pts + (ws.rstart[ri] + (lo - pre)), (hi - lo) * 16u, &ws.mbar);
-  }
-  for (int ri = 0; ri < R; ri++) {
-    const uint32_t pre = ws.rpre[ri], nxt = ws.rpre[ri + 1];
-    if (nxt <= c0) continue;
-    if (pre >= c1) break;
-    const uint32_t lo = max(pre, c0), hi = min(nxt, c1), s = ws.rstart[ri];
-    for (uint32_t ge = lo + lane; ge < hi; ge += 32) ws.pos[ge - c0] = (int)(s + (ge - pre));
   }
   unsigned int spins = 0;
   while (!mbar_try_wait(&ws.mbar, phase)) {
@@ -234,14 +226,14 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
             const float d = sqdist_ref(mx, my, mz, cand[t].x, cand[t].y, cand[t].z);
             if (e < nch && d < bd) { bd = d; be = e; }
           }
-          int bp = be >= 0 ? ws.pos[be] : -1;
+          int bp = be >= 0 ? __float_as_int(ws.pts[be].w) : -1;
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) {
             const float od = __shfl_xor_sync(FULL, bd, off);
             const int op = __shfl_xor_sync(FULL, bp, off);
-            if (TK::before(od, op, bd, bp, g.pts)) { bd = od; bp = op; }
+            if (TK::before(od, op, bd, bp)) { bd = od; bp = op; }
           }
-          if ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1)) && bp >= 0 && bd <= best.worst()) best.offer(bd, bp, g.pts);
+          if ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1)) && bp >= 0 && bd <= best.worst()) best.offer(bd, bp);
         }
         __syncwarp();
       }
@@ -260,7 +252,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           for (int e = lane; e < nch; e += 32) {
             const float4 p = ws.pts[e];
             const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
-            if (d <= part.worst()) part.offer(d, ws.pos[e], g.pts);
+            if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
           }
           __syncwarp();
         }
@@ -273,7 +265,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           for (int off = 16; off > 0; off >>= 1) {
             const float od = __shfl_xor_sync(FULL, gd, off);
             const int op = __shfl_xor_sync(FULL, gp, off);
-            if (TK::before(od, op, gd, gp, g.pts)) { gd = od; gp = op; }
+            if (TK::before(od, op, gd, gp)) { gd = od; gp = op; }
           }
           if (gp >= 0 && gp == part.p[0]) part.pop_front();
           if (mine) best.append_shift(gd, gp);   // K appends leave the list in ascending order
@@ -288,7 +280,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           for (int e = 0; e < nch; e++) {
             const float4 p = ws.pts[e];
             const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= best.worst()) best.offer(d, ws.pos[e], g.pts);
+            if (d <= best.worst()) best.offer(d, __float_as_int(p.w));
           }
         }
         __syncwarp();
@@ -306,7 +298,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           for (int e = sub; e < nch; e += LPQ) {
             const float4 p = ws.pts[e];
             const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= part.worst()) part.offer(d, ws.pos[e], g.pts);
+            if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
           }
         }
         __syncwarp();
@@ -319,7 +311,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
         for (int off = LPQ / 2; off > 0; off >>= 1) {
           const float od = __shfl_xor_sync(FULL, gd, off);
           const int op = __shfl_xor_sync(FULL, gp, off);
-          if (TK::before(od, op, gd, gp, g.pts)) { gd = od; gp = op; }
+          if (TK::before(od, op, gd, gp)) { gd = od; gp = op; }
         }
         if (gp >= 0 && gp == part.p[0]) part.pop_front();
         if (member) best.append_shift(gd, gp);
