@@ -175,14 +175,20 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
       const int4 v = __ldg(reinterpret_cast<const int4*>(row) + i / 4);
       id[i] = v.x; id[i + 1] = v.y; id[i + 2] = v.z; id[i + 3] = v.w;
     }
-    float4 nb[K > 0 ? K : 1];
+    // gathers in batches of kBatch: enough loads in flight per thread, few enough registers for ~40 warps per SM
+    // (the kernel is bound by the fp64 pipe and needs the occupancy to keep it fed)
+    constexpr int kBatch = (K > 0 && K % 8 == 0) ? 8 : 4;
 #pragma unroll
-    for (int i = 0; i < K; i++) nb[i] = __ldg(pts + id[i]);
+    for (int b0 = 0; b0 < K; b0 += kBatch) {
+      float4 nb[kBatch];
 #pragma unroll
-    for (int i = 0; i < K; i++) {
-      const double dx = (double)nb[i].x - ox, dy = (double)nb[i].y - oy, dz = (double)nb[i].z - oz;
-      sx += dx; sy += dy; sz += dz;
-      sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
+      for (int i = 0; i < kBatch; i++) nb[i] = __ldg(pts + id[b0 + i]);
+#pragma unroll
+      for (int i = 0; i < kBatch; i++) {
+        const double dx = (double)nb[i].x - ox, dy = (double)nb[i].y - oy, dz = (double)nb[i].z - oz;
+        sx += dx; sy += dy; sz += dz;
+        sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
+      }
     }
   } else {
     for (int i = 0; i < k; i++) {

@@ -80,4 +80,6 @@ def spectral_gap_ok(points, idx, rel=1e-2):
     c = nb - nb.mean(1, keepdims=True)
     cov = np.einsum("nki,nkj->nij", c, c) / idx.shape[1]
     w = np.linalg.eigvalsh(cov)
-    return (w[:, 1] - w[:, 0]) > rel * w[:, 2]
+    # an exactly singular neighbourhood (smallest singular value == 0, e.g. all z identical) leaves the sign of the
+    # last singular vectors of U and V independent of each other, so U diag(1,1,eps) V^T is arbitrary there too
+    return ((w[:, 1] - w[:, 0]) > rel * w[:, 2]) & (w[:, 0] > 1e-12 * w[:, 2])
