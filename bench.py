@@ -55,6 +55,15 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) are sent to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 # ------------------------------------------------------------------------------------------- data
 def make_workload(seed: int):
     """(submap (1M,3), keyframe bounds, list of 8 perturbed world-frame scans (65536,3))."""
@@ -121,8 +130,8 @@ def cpu_register_stream(tgt, bounds, scans, steps, warmup):
     """The reference's CPU path on the same workload. Returns (scans/s, description)."""
     import oracle
     variant = "ref" if oracle.available("ref") else "port"
-    o = configure(oracle.OracleGICP(variant))
-    threads = oracle.lib(variant).orc_max_threads()
+    threads = os.cpu_count() or 1          # all host cores, whatever OMP_NUM_THREADS torchrun put in the environment
+    o = configure(oracle.OracleGICP(variant, num_threads=threads))
     # submap: per-keyframe covariances computed once and concatenated (covariance reuse), then the tree
     covs = []
     for s, e in zip(bounds[:-1], bounds[1:]):
@@ -151,7 +160,7 @@ def run_reference(args, rank):
             "data": "synthetic", "config": workload_config(1),
             "cpu_baseline": {"value": val, "unit": "scans/s", "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(world):
@@ -289,8 +298,11 @@ def run_gpu(args, rank, local_rank, world):
     # ---- judged bulk numbers: K3 on a bulk keyframe batch (BASELINE config 3 shape, bounded to 64 keyframes per GPU)
     bulk = bulk_covariance(g, scans, hbm)
 
-    # ---- CPU baseline beside it (bounded sample, all host cores)
-    cpu_val, cpu_ms, threads, kind, desc = cpu_register_stream(tgt, bounds, scans, 10, 2)
+    # ---- CPU baseline beside it (bounded sample, all host cores) — rank 0 at N=1 only
+    cpu = None
+    if world == 1:
+        cpu_val, cpu_ms, threads, kind, desc = cpu_register_stream(tgt, bounds, scans, 10, 2)
+        cpu = {"value": cpu_val, "unit": "scans/s", "ms_per_step": cpu_ms, "cores": threads, "kind": kind, "sample": desc}
 
     line = {
         "metric": "gicp_scan_to_submap_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -301,9 +313,9 @@ def run_gpu(args, rank, local_rank, world):
                 "d2h_bytes_per_step": int(8 + np.mean(iters[W:]) * (29 * 8 + 2 * 8) + 64)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "kernels": kernels, "bulk": bulk,
-        "cpu_baseline": {"value": cpu_val, "unit": "scans/s", "ms_per_step": cpu_ms, "cores": threads, "kind": kind, "sample": desc},
+        "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -19,6 +19,8 @@ constexpr int kMortonBits = 3 * kBitsPerAxis;     // 36
 constexpr int kTopLevel = kBitsPerAxis;           // one cell spans the whole grid at this level
 constexpr int kNumLevels = kTopLevel + 1;         // levels 0..12
 constexpr int kMaxSegBits = 20;                   // keyframes per batched index
+constexpr int kSortLevel = 3;                     // keys are sorted on the bits of levels >= 3 only (27 of 36 bits):
+                                                  // one radix pass less; cells finer than that are never needed
 constexpr int kMaxCoord = (1 << kBitsPerAxis) - 1;
 constexpr unsigned long long kEmptyKey = ~0ull;
 

@@ -22,11 +22,14 @@ __device__ __forceinline__ float ord2f(unsigned int o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
-__global__ void set_pair_kernel(int* p, int a, int b) { p[0] = a; p[1] = b; }
-
-__global__ void bbox_init_kernel(unsigned int* lo, unsigned int* hi, int n_seg) {
+// one launch that resets everything the build accumulates into: bounding boxes, the sort's digit totals, and
+// (single-keyframe builds) the segment table, which then needs no host buffer and no sync on the per-scan path
+__global__ void __launch_bounds__(256) index_prep_kernel(unsigned int* lo, unsigned int* hi, int n_seg, uint32_t* digit_hist, int n_hist,
+                                                        int* seg_start, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * n_seg) { lo[i] = 0xffffffffu; hi[i] = 0u; }
+  if (i < n_hist) digit_hist[i] = 0u;
+  if (seg_start && i == 0) { seg_start[0] = 0; seg_start[1] = n; }
 }
 
 // per-segment bounding boxes. Warp-aggregated when the whole warp sits in one segment.
@@ -61,8 +64,26 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ xyz
   }
 }
 
+// power-of-two level-0 cell size with 4096*h0 strictly larger than the largest bbox extent
+__device__ __forceinline__ float cell_size_for(float e) {
+  if (!(e > 9.765625e-4f)) e = 9.765625e-4f;  // degenerate clouds: keep a sane cell size
+  if (!(e < 1e30f)) e = 1e30f;
+  int ex;
+  frexpf(e * 1.01f, &ex);                     // e*1.01 < 2^ex
+  return ldexpf(1.0f, ex - kBitsPerAxis);
+}
+__device__ __forceinline__ void write_meta(GridMeta* meta, float h0) {
+  meta->h0 = h0;
+  meta->inv_h0 = 1.0f / h0;                   // exact: power of two
+  meta->margin = h0 * (1.0f / 512.0f);
+  meta->base_level = 0;
+  meta->cells_total = 0;
+  for (int i = 0; i < 16; i++) meta->level_hist[i] = 0;
+}
+
 // One block. Segment origins = lower bbox corners; one common power-of-two cell size h0 with
-// 4096*h0 strictly larger than the largest extent of any segment.
+// 4096*h0 strictly larger than the largest extent of any segment. (Multi-keyframe builds only; a
+// single-keyframe build derives the same values inside keys_kernel.)
 __global__ void __launch_bounds__(256) grid_meta_kernel(const unsigned int* __restrict__ lo, const unsigned int* __restrict__ hi, int n_seg,
                                                         float4* __restrict__ seg_origin, GridMeta* __restrict__ meta) {
   __shared__ float smax[256];
@@ -78,46 +99,46 @@ __global__ void __launch_bounds__(256) grid_meta_kernel(const unsigned int* __re
     if (threadIdx.x < off) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + off]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    float e = smax[0];
-    if (!(e > 9.765625e-4f)) e = 9.765625e-4f;  // degenerate clouds: keep a sane cell size
-    if (!(e < 1e30f)) e = 1e30f;
-    int ex;
-    frexpf(e * 1.01f, &ex);                    // e*1.01 < 2^ex
-    const float h0 = ldexpf(1.0f, ex - kBitsPerAxis);
-    meta->h0 = h0;
-    meta->inv_h0 = 1.0f / h0;                  // exact: power of two
-    meta->margin = h0 * (1.0f / 512.0f);
-    meta->base_level = 0;
-    meta->cells_total = 0;
-    for (int i = 0; i < 16; i++) meta->level_hist[i] = 0;
-  }
+  if (threadIdx.x == 0) write_meta(meta, cell_size_for(smax[0]));
 }
 
+// voxel keys + (fused) the radix sort's digit totals for every pass. Single-keyframe builds also derive the grid
+// parameters here, every thread from the same six bbox words, so no separate one-block launch sits on the path.
 __global__ void __launch_bounds__(256) keys_kernel(const float* __restrict__ xyz, int stride, int n, const int* __restrict__ seg_start, int n_seg,
-                                                   const float4* __restrict__ seg_origin, const GridMeta* __restrict__ meta,
-                                                   unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                   float4* __restrict__ seg_origin, GridMeta* __restrict__ meta,
+                                                   const unsigned int* __restrict__ lo, const unsigned int* __restrict__ hi,
+                                                   unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                   uint32_t* __restrict__ digit_hist, int low_bit, int passes) {
+  __shared__ uint32_t hsm[8 * kSortRadix];
+  for (int t = threadIdx.x; t < passes * kSortRadix; t += blockDim.x) hsm[t] = 0;
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int seg = find_segment(seg_start, n_seg, i);
-  const float4 o = __ldg(seg_origin + seg);
-  const float inv_h0 = __ldg(&meta->inv_h0);
-  const float x = xyz[(size_t)i * stride + 0], y = xyz[(size_t)i * stride + 1], z = xyz[(size_t)i * stride + 2];
-  const unsigned int cx = clampi(voxel_coord_unclamped(x, o.x, inv_h0), 0, kMaxCoord);
-  const unsigned int cy = clampi(voxel_coord_unclamped(y, o.y, inv_h0), 0, kMaxCoord);
-  const unsigned int cz = clampi(voxel_coord_unclamped(z, o.z, inv_h0), 0, kMaxCoord);
-  keys[i] = ((unsigned long long)seg << kMortonBits) | morton3(cx, cy, cz);
-  vals[i] = (uint32_t)i;
-}
-
-__global__ void __launch_bounds__(256) gather_points_kernel(const float* __restrict__ xyz, int stride, int n, const uint32_t* __restrict__ vals,
-                                                            float4* __restrict__ pts, int* __restrict__ inv) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const uint32_t i = vals[j];
-  const float* p = xyz + (size_t)i * stride;
-  pts[j] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
-  inv[i] = j;
+  if (i < n) {
+    int seg = 0;
+    float4 o;
+    float inv_h0;
+    if (n_seg == 1) {
+      o = make_float4(ord2f(lo[0]), ord2f(lo[1]), ord2f(lo[2]), 0.f);
+      const float h0 = cell_size_for(fmaxf(ord2f(hi[0]) - o.x, fmaxf(ord2f(hi[1]) - o.y, ord2f(hi[2]) - o.z)));
+      inv_h0 = 1.0f / h0;
+      if (i == 0) { seg_origin[0] = o; write_meta(meta, h0); }
+    } else {
+      seg = find_segment(seg_start, n_seg, i);
+      o = seg_origin[seg];
+      inv_h0 = meta->inv_h0;
+    }
+    const float x = xyz[(size_t)i * stride + 0], y = xyz[(size_t)i * stride + 1], z = xyz[(size_t)i * stride + 2];
+    const unsigned int cx = clampi(voxel_coord_unclamped(x, o.x, inv_h0), 0, kMaxCoord);
+    const unsigned int cy = clampi(voxel_coord_unclamped(y, o.y, inv_h0), 0, kMaxCoord);
+    const unsigned int cz = clampi(voxel_coord_unclamped(z, o.z, inv_h0), 0, kMaxCoord);
+    const unsigned long long key = ((unsigned long long)seg << kMortonBits) | morton3(cx, cy, cz);
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    for (int p = 0; p < passes; p++) atomicAdd(&hsm[p * kSortRadix + sort_digit_of(key, low_bit, p)], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < passes * kSortRadix; t += blockDim.x)
+    if (hsm[t]) atomicAdd(&digit_hist[t], hsm[t]);
 }
 
 // first level at which two keys fall into different cells, +1; kNumLevels (13) if they differ at the top
@@ -128,11 +149,20 @@ __device__ __forceinline__ int diff_levels(unsigned long long a, unsigned long l
   return min(msb / 3 + 1, kNumLevels);
 }
 
-__global__ void __launch_bounds__(256) level_hist_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta) {
+// reorder the points into Morton order (+ inverse permutation) and, in the same pass over the sorted keys, count at
+// which octree level every sorted position opens a new cell
+__global__ void __launch_bounds__(256) gather_levels_kernel(const float* __restrict__ xyz, int stride, int n, const uint32_t* __restrict__ vals,
+                                                            const unsigned long long* __restrict__ keys, float4* __restrict__ pts,
+                                                            int* __restrict__ inv, GridMeta* __restrict__ meta) {
   __shared__ unsigned int h[16];
   if (threadIdx.x < 16) h[threadIdx.x] = 0;
   __syncthreads();
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const uint32_t i = vals[j];
+    const float* p = xyz + (size_t)i * stride;
+    pts[j] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
+    inv[i] = j;
     const int d = j == 0 ? kNumLevels : diff_levels(keys[j], keys[j - 1]);
     if (d) atomicAdd(&h[d], 1u);
   }
@@ -142,8 +172,9 @@ __global__ void __launch_bounds__(256) level_hist_kernel(const unsigned long lon
 
 // cells(L) = #positions with diff_levels > L. Base level = finest level whose mean occupancy is
 // >= occupancy and whose cumulative entry count (this level and all coarser ones) fits the table.
-__global__ void choose_base_kernel(GridMeta* meta, int n, unsigned int max_entries, int occupancy) {
-  if (threadIdx.x || blockIdx.x) return;
+// The keys are only sorted down to level kSortLevel (finer bits stay in input order inside a cell), so cells are
+// contiguous ranges for levels >= kSortLevel and the base level is never finer than that.
+__device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned int max_entries, int occupancy, unsigned int* total_out) {
   unsigned int cells[kNumLevels];
   unsigned int acc = 0;
   for (int L = kTopLevel; L >= 0; L--) {
@@ -152,21 +183,28 @@ __global__ void choose_base_kernel(GridMeta* meta, int n, unsigned int max_entri
   }
   int base = kTopLevel;
   unsigned int total = cells[kTopLevel];
-  for (int L = kTopLevel - 1; L >= 0; L--) {
+  for (int L = kTopLevel - 1; L >= kSortLevel; L--) {
     if ((unsigned long long)cells[L] * (unsigned)occupancy > (unsigned long long)n) break;
     if (total + cells[L] > max_entries) break;
     total += cells[L];
     base = L;
   }
-  meta->base_level = base;
-  meta->cells_total = total;
+  if (total_out) *total_out = total;
+  return base;
 }
 
-__global__ void __launch_bounds__(256) table_insert_kernel(const unsigned long long* __restrict__ keys, int n, const GridMeta* __restrict__ meta,
-                                                           CellSlot* __restrict__ table, uint32_t mask) {
+__global__ void __launch_bounds__(256) table_insert_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta,
+                                                           CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy) {
+  __shared__ int s_base;
+  if (threadIdx.x == 0) {
+    unsigned int total;
+    s_base = choose_base(meta, n, max_entries, occupancy, &total);
+    if (blockIdx.x == 0) { meta->base_level = s_base; meta->cells_total = total; }   // published for every later kernel
+  }
+  __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const int base = meta->base_level;
+  const int base = s_base;
   const unsigned long long k = keys[j];
   const int d = j == 0 ? kNumLevels : diff_levels(k, keys[j - 1]);
   for (int L = base; L < d; L++) {
@@ -205,13 +243,7 @@ inline int ceil_log2(unsigned int v) { int b = 0; while ((1u << b) < v) b++; ret
 
 void free_index(Index* idx, cudaStream_t stream) {
   if (!idx) return;
-  dev_free(idx->pts, stream);
-  dev_free(idx->inv, stream);
-  dev_free(idx->keys, stream);
-  dev_free(idx->table, stream);
-  dev_free(idx->meta, stream);
-  dev_free(idx->seg_origin, stream);
-  dev_free(idx->seg_start, stream);
+  dev_free(idx->arena, stream);
   delete idx;
 }
 
@@ -236,42 +268,52 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   for (int i = 0; i < n_seg; i++)
     if (seg32[i + 1] <= seg32[i]) { delete idx; return fail(h, NGICP_ERR_INVALID, "index build: empty or unordered segment"); }
 
-  const int nbits = kMortonBits + (n_seg > 1 ? ceil_log2((unsigned)n_seg) : 0);
+  const int low_bit = 3 * kSortLevel;
+  const int nbits = kMortonBits - low_bit + (n_seg > 1 ? ceil_log2((unsigned)n_seg) : 0);
+  const int passes = sort_num_passes(nbits);
   unsigned int cap = 1024;
   while (cap < (unsigned long long)n + n / 2) cap <<= 1;
   idx->table_mask = cap - 1;
 
-  unsigned long long *keys_a = nullptr, *keys_b = nullptr, *keys_sorted = nullptr;
-  uint32_t *vals_a = nullptr, *vals_b = nullptr, *vals_sorted = nullptr, *sort_scratch = nullptr;
-  unsigned int* bbox = nullptr;
-  auto cleanup = [&]() {
-    dev_free(keys_b, s); dev_free(vals_a, s); dev_free(vals_b, s); dev_free(sort_scratch, s); dev_free(bbox, s);
-  };
+  // two stream-ordered allocations per build: the index's own arena and one scratch block
+  auto align_up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_pts = 0, o_inv = o_pts + align_up(sizeof(float4) * (size_t)n), o_keys = o_inv + align_up(sizeof(int) * (size_t)n),
+               o_table = o_keys + align_up(sizeof(unsigned long long) * (size_t)n), o_meta = o_table + align_up(sizeof(CellSlot) * (size_t)cap),
+               o_sego = o_meta + align_up(sizeof(GridMeta)), o_segs = o_sego + align_up(sizeof(float4) * (size_t)n_seg),
+               arena_bytes = o_segs + align_up(sizeof(int) * ((size_t)n_seg + 1));
+  const size_t scratch_elems = sort_scratch_elems(n, nbits);
+  const size_t s_keys = 0, s_vals_a = s_keys + align_up(sizeof(unsigned long long) * (size_t)n), s_vals_b = s_vals_a + align_up(sizeof(uint32_t) * (size_t)n),
+               s_sort = s_vals_b + align_up(sizeof(uint32_t) * (size_t)n), s_bbox = s_sort + align_up(sizeof(uint32_t) * scratch_elems),
+               scratch_bytes = s_bbox + align_up(sizeof(unsigned int) * 6 * (size_t)n_seg);
+  char* scratch = nullptr;
 #define IDX_CUDA(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t _e = (expr);                                                                             \
     if (_e != cudaSuccess) {                                                                             \
-      cleanup(); dev_free(keys_a, s); idx->keys = nullptr; free_index(idx, s);                           \
+      dev_free(scratch, s); free_index(idx, s);                                                          \
       return fail(h, NGICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     }                                                                                                    \
   } while (0)
+  IDX_CUDA(dev_alloc(&idx->arena, arena_bytes, s));
+  IDX_CUDA(dev_alloc(&scratch, scratch_bytes, s));
+  idx->pts = reinterpret_cast<float4*>(idx->arena + o_pts);
+  idx->inv = reinterpret_cast<int*>(idx->arena + o_inv);
+  idx->keys = reinterpret_cast<unsigned long long*>(idx->arena + o_keys);
+  idx->table = reinterpret_cast<CellSlot*>(idx->arena + o_table);
+  idx->meta = reinterpret_cast<GridMeta*>(idx->arena + o_meta);
+  idx->seg_origin = reinterpret_cast<float4*>(idx->arena + o_sego);
+  idx->seg_start = reinterpret_cast<int*>(idx->arena + o_segs);
+  unsigned long long* keys_tmp = reinterpret_cast<unsigned long long*>(scratch + s_keys);
+  uint32_t* vals_a = reinterpret_cast<uint32_t*>(scratch + s_vals_a);
+  uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + s_vals_b);
+  uint32_t* sort_scratch = reinterpret_cast<uint32_t*>(scratch + s_sort);
+  unsigned int* lo = reinterpret_cast<unsigned int*>(scratch + s_bbox);
+  unsigned int* hi = lo + 3 * n_seg;
+  // the sort ping-pongs; start in whichever buffer makes the LAST pass land in the arena
+  unsigned long long* keys_a = (passes % 2 == 0) ? idx->keys : keys_tmp;
+  unsigned long long* keys_b = (passes % 2 == 0) ? keys_tmp : idx->keys;
 
-  IDX_CUDA(dev_alloc(&idx->pts, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&idx->inv, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&idx->table, (size_t)cap, s));
-  IDX_CUDA(dev_alloc(&idx->meta, 1, s));
-  IDX_CUDA(dev_alloc(&idx->seg_origin, (size_t)n_seg, s));
-  IDX_CUDA(dev_alloc(&idx->seg_start, (size_t)n_seg + 1, s));
-  IDX_CUDA(dev_alloc(&keys_a, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&keys_b, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&vals_a, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&vals_b, (size_t)n, s));
-  IDX_CUDA(dev_alloc(&sort_scratch, sort_scratch_elems(n, nbits), s));
-  IDX_CUDA(dev_alloc(&bbox, (size_t)6 * n_seg, s));
-  if (n_seg == 1) {
-    set_pair_kernel<<<1, 1, 0, s>>>(idx->seg_start, 0, n);  // no host buffer, no sync on the per-scan path
-    count_launch(h);
-  } else {
+  if (n_seg > 1) {
     IDX_CUDA(cudaMemcpyAsync(idx->seg_start, seg32.data(), sizeof(int) * (n_seg + 1), cudaMemcpyHostToDevice, s));
     IDX_CUDA(cudaStreamSynchronize(s));  // seg32 is a stack-lifetime buffer
   }
@@ -279,24 +321,29 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
 
   const int tpb = 256;
   const int nb = (n + tpb - 1) / tpb;
-  unsigned int *lo = bbox, *hi = bbox + 3 * n_seg;
-  bbox_init_kernel<<<(3 * n_seg + 255) / 256, 256, 0, s>>>(lo, hi, n_seg);
+  const int n_hist = passes * kSortRadix;
+  index_prep_kernel<<<(std::max(3 * n_seg, n_hist) + 255) / 256, 256, 0, s>>>(lo, hi, n_seg, sort_scratch, n_hist, n_seg == 1 ? idx->seg_start : nullptr, n);
   bbox_kernel<<<std::min(nb, 148 * 8), tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, lo, hi);
-  grid_meta_kernel<<<1, 256, 0, s>>>(lo, hi, n_seg, idx->seg_origin, idx->meta);
-  keys_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, idx->seg_origin, idx->meta, keys_a, vals_a);
-  count_launch(h, 4);
-  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, nbits, s, &keys_sorted, &vals_sorted));
-  gather_points_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, idx->pts, idx->inv);
-  level_hist_kernel<<<std::min(nb, 148 * 8), tpb, 0, s>>>(keys_sorted, n, idx->meta);
-  choose_base_kernel<<<1, 32, 0, s>>>(idx->meta, n, cap / 2, 2);
-  table_insert_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask);
+  count_launch(h, 2);
+  if (n_seg > 1) {
+    grid_meta_kernel<<<1, 256, 0, s>>>(lo, hi, n_seg, idx->seg_origin, idx->meta);
+    count_launch(h);
+  }
+  keys_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, idx->seg_origin, idx->meta, lo, hi, keys_a, vals_a, sort_scratch, low_bit, passes);
+  count_launch(h);
+  unsigned long long* keys_sorted = nullptr;
+  uint32_t* vals_sorted = nullptr;
+  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, low_bit, nbits, s, &keys_sorted, &vals_sorted, true));
+  if (keys_sorted != idx->keys) {  // n == 1: nothing was sorted
+    IDX_CUDA(cudaMemcpyAsync(idx->keys, keys_sorted, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    keys_sorted = idx->keys;
+  }
+  gather_levels_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, keys_sorted, idx->pts, idx->inv, idx->meta);
+  table_insert_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, cap / 2, 2);
   table_close_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask);
-  count_launch(h, 5);
+  count_launch(h, 3);
   IDX_CUDA(cudaGetLastError());
-  // keep the sorted keys, drop the other ping-pong buffer
-  idx->keys = keys_sorted;
-  if (keys_sorted == keys_a) { /* keys_b freed by cleanup */ } else { dev_free(keys_a, s); keys_b = nullptr; }
-  cleanup();
+  dev_free(scratch, s);
 #undef IDX_CUDA
   *out = idx;
   return NGICP_OK;

@@ -32,6 +32,7 @@ struct ngicp_index {
   int device = 0;
   int n = 0;
   int n_seg = 1;
+  char* arena = nullptr;                  // one allocation holding every array below
   float4* pts = nullptr;                  // [n] Morton-sorted, .w = original index
   int* inv = nullptr;                     // [n] original index -> sorted position
   unsigned long long* keys = nullptr;     // [n] sorted voxel keys

@@ -14,36 +14,18 @@ namespace ngicp {
 
 namespace {
 
-__global__ void __launch_bounds__(256) sort_histogram_kernel(const unsigned long long* __restrict__ keys, int n, int passes,
+__global__ void __launch_bounds__(256) sort_histogram_kernel(const unsigned long long* __restrict__ keys, int n, int low_bit, int passes,
                                                              uint32_t* __restrict__ digit_hist) {
   __shared__ uint32_t h[8 * kSortRadix];
   for (int i = threadIdx.x; i < passes * kSortRadix; i += blockDim.x) h[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
-    for (int p = 0; p < passes; p++) atomicAdd(&h[p * kSortRadix + (int)((k >> (p * kSortRadixBits)) & (kSortRadix - 1))], 1u);
+    for (int p = 0; p < passes; p++) atomicAdd(&h[p * kSortRadix + sort_digit_of(k, low_bit, p)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < passes * kSortRadix; i += blockDim.x)
     if (h[i]) atomicAdd(&digit_hist[i], h[i]);
-}
-
-// one block of 256 threads; exclusive scan of each pass's 256 digit totals, in place
-__global__ void __launch_bounds__(256) sort_digit_starts_kernel(uint32_t* __restrict__ digit_hist, int passes) {
-  __shared__ uint32_t s[kSortRadix];
-  for (int p = 0; p < passes; p++) {
-    const uint32_t v = digit_hist[p * kSortRadix + threadIdx.x];
-    s[threadIdx.x] = v;
-    __syncthreads();
-    for (int off = 1; off < kSortRadix; off <<= 1) {
-      const uint32_t t = threadIdx.x >= off ? s[threadIdx.x - off] : 0u;
-      __syncthreads();
-      s[threadIdx.x] += t;
-      __syncthreads();
-    }
-    digit_hist[p * kSortRadix + threadIdx.x] = s[threadIdx.x] - v;
-    __syncthreads();
-  }
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_count_kernel(const unsigned long long* __restrict__ keys, int n, int shift,
@@ -88,8 +70,8 @@ __global__ void __launch_bounds__(256) sort_scan_rows_kernel(uint32_t* __restric
 
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                    unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                                   const uint32_t* __restrict__ counts, const uint32_t* __restrict__ digit_start,
-                                                                   int n, int shift, int nblocks) {
+                                                                   const uint32_t* __restrict__ counts, const uint32_t* __restrict__ digit_total,
+                                                                   int n, int shift, int nblocks, int rows_scanned) {
   constexpr int kWarps = kSortThreads / 32;
   __shared__ uint32_t warp_cnt[kWarps][kSortRadix];
   __shared__ uint32_t digit_base[kSortRadix];
@@ -97,7 +79,24 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int w = 0; w < kWarps; w++) warp_cnt[w][threadIdx.x] = 0;
-  digit_base[threadIdx.x] = digit_start[threadIdx.x] + counts[threadIdx.x * nblocks + blockIdx.x];
+  {
+    // global start of this thread's digit = exclusive scan of the 256 raw digit totals of the pass
+    const uint32_t v = digit_total[threadIdx.x];
+    digit_base[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < kSortRadix; off <<= 1) {
+      const uint32_t t = threadIdx.x >= off ? digit_base[threadIdx.x - off] : 0u;
+      __syncthreads();
+      digit_base[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t row = 0;  // keys with this digit in earlier tiles
+    if (rows_scanned) row = counts[threadIdx.x * nblocks + blockIdx.x];
+    else for (int b = 0; b < (int)blockIdx.x; b++) row += counts[threadIdx.x * nblocks + b];
+    const uint32_t start = digit_base[threadIdx.x] - v;
+    __syncthreads();
+    digit_base[threadIdx.x] = start + row;
+  }
   __syncthreads();
 
   const int chunk0 = blockIdx.x * kSortTile + warp * (32 * kSortItems);
@@ -150,29 +149,31 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
 }  // namespace
 
 int radix_sort_pairs(unsigned long long* keys_a, uint32_t* vals_a, unsigned long long* keys_b, uint32_t* vals_b,
-                     uint32_t* scratch, int n, int nbits, cudaStream_t stream,
-                     unsigned long long** out_keys, uint32_t** out_vals) {
+                     uint32_t* scratch, int n, int low_bit, int nbits, cudaStream_t stream,
+                     unsigned long long** out_keys, uint32_t** out_vals, bool hist_ready) {
   *out_keys = keys_a;
   *out_vals = vals_a;
   if (n <= 1 || nbits <= 0) return 0;
   const int passes = sort_num_passes(nbits);
   const int nblocks = sort_num_blocks(n);
-  uint32_t* digit_hist = scratch;                       // [passes][256]
+  uint32_t* digit_hist = scratch;                       // [passes][256] raw digit totals
   uint32_t* counts = scratch + passes * kSortRadix;     // [256][nblocks]
   int launches = 0;
-  cudaMemsetAsync(digit_hist, 0, sizeof(uint32_t) * passes * kSortRadix, stream);
-  const int hist_blocks = max(1, min(nblocks, 148 * 4));
-  sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, passes, digit_hist);
-  sort_digit_starts_kernel<<<1, 256, 0, stream>>>(digit_hist, passes);
-  launches += 2;
+  if (!hist_ready) {
+    cudaMemsetAsync(digit_hist, 0, sizeof(uint32_t) * passes * kSortRadix, stream);
+    const int hist_blocks = max(1, min(nblocks, 148 * 4));
+    sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, low_bit, passes, digit_hist);
+    launches += 1;
+  }
+  const bool scan_rows = nblocks > 64;   // few tiles: the scatter kernel sums the earlier tiles itself
   unsigned long long* kin = keys_a; uint32_t* vin = vals_a;
   unsigned long long* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; p++) {
-    const int shift = p * kSortRadixBits;
+    const int shift = low_bit + p * kSortRadixBits;
     sort_count_kernel<<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks);
-    sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
-    sort_scatter_kernel<<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks);
-    launches += 3;
+    if (scan_rows) sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
+    sort_scatter_kernel<<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+    launches += scan_rows ? 3 : 2;
     unsigned long long* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

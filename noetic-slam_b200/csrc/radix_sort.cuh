@@ -20,11 +20,17 @@ inline size_t sort_scratch_elems(int n, int nbits) {
   return (size_t)sort_num_passes(nbits) * kSortRadix + (size_t)kSortRadix * sort_num_blocks(n) + 64;
 }
 
-// Sorts n pairs by key bits [0, nbits). (keys_a, vals_a) hold the input; (keys_b, vals_b) are
+// Sorts n pairs by key bits [low_bit, low_bit + nbits). (keys_a, vals_a) hold the input; (keys_b, vals_b) are
 // ping-pong buffers of the same size. On return *out_keys / *out_vals point at whichever pair
-// holds the sorted result. Returns the number of kernels launched.
+// holds the sorted result (pair A after an even number of passes, pair B after an odd number).
+// hist_ready: the caller already accumulated the raw per-pass digit totals into scratch[0 .. passes*256)
+// (sort_digit_of gives the digit), which saves the histogram launch. Returns the number of kernels launched.
 int radix_sort_pairs(unsigned long long* keys_a, uint32_t* vals_a, unsigned long long* keys_b, uint32_t* vals_b,
-                     uint32_t* scratch, int n, int nbits, cudaStream_t stream,
-                     unsigned long long** out_keys, uint32_t** out_vals);
+                     uint32_t* scratch, int n, int low_bit, int nbits, cudaStream_t stream,
+                     unsigned long long** out_keys, uint32_t** out_vals, bool hist_ready);
+
+__host__ __device__ __forceinline__ int sort_digit_of(unsigned long long key, int low_bit, int pass) {
+  return (int)((key >> (low_bit + pass * kSortRadixBits)) & (kSortRadix - 1));
+}
 
 }  // namespace ngicp
