@@ -198,6 +198,7 @@ int ngicp_create(int device, ngicp_handle** out) {
   if (const char* e = std::getenv("NGICP_K2_CMAX_MULT")) h->k2_cmax_mult = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("NGICP_K2_LPQ")) h->k2_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_LPQ")) h->k4_lpq = std::atoi(e);
+  if (const char* e = std::getenv("NGICP_K4_BALL")) h->k4_ball = std::atoi(e);
   for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // setIdentity, lsq_registration.cc:65
 #define CREATE_CUDA(expr)                                                                     \
   do {                                                                                        \

@@ -59,6 +59,7 @@ struct ngicp_handle {
   // registration scratch
   int* corr = nullptr;          // [n_src] target sorted position or -1 (order: source sorted position)
   size_t corr_cap = 0;
+  size_t corr_n = 0;            // number of source points the cached correspondences belong to
   double lin_pose[12];          // pose of the last linearize (R row-major 9 + t 3), needed by compute_error
   bool lin_valid = false;
   double* partials = nullptr;   // [max_blocks][32] block partial sums
@@ -77,6 +78,7 @@ struct ngicp_handle {
   int k2_cmax_mult = 4;
   int k2_lpq = 0;   // lanes per query in K2 (0 = pick by cloud size)
   int k4_lpq = 0;
+  int k4_ball = 1;  // seed re-association with the previous correspondences (NGICP_K4_BALL=0 disables)
   // LM state (lsq_registration.h:151-168)
   double lm_lambda = -1.0;
   double final_hessian[36];

@@ -137,7 +137,7 @@ __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* _
 
 // K4. grid = (blocks per scan, scans). Source scan b = source segment b; its target segment is
 // target_seg[b] (or 0).
-template <bool WANT_HB, int LPQ>
+template <bool WANT_HB, int LPQ, bool USE_PREV>
 __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
                                                                  PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ target_seg,
                                                                  double thr2, float max_sqd, int cmax, int* __restrict__ corr,
@@ -164,12 +164,26 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
 #pragma unroll
     for (int r = 0; r < 3; r++)
       qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
+    // Re-association after a small pose update: the previous nearest neighbour, re-measured at the new pose, bounds
+    // the search to a small ball (wknn.cuh: ball_search). Same exact result, a fraction of the work.
+    bool resolved = false;
+    float nd = __int_as_float(0x7f800000);
+    int ni = -1;
+    if (USE_PREV && active) {
+      const int c = corr[j];
+      const int prev = c >= 0 ? c : (c <= -2 ? -2 - c : -1);   // gated-out neighbours are remembered as -2-pos
+      if (prev >= 0) {
+        const float4 pb0 = __ldg(tgt.pts + prev);
+        resolved = ball_search<LPQ>(tgt, qf[0], qf[1], qf[2], tseg, sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z), __float_as_int(pb0.w), nd, ni);
+      }
+    }
     TopK<1> best;
-    warp_knn<LPQ>(tgt, active, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
-    const int pos = best.p[0] >= 0 ? __ldg(tgt.inv + best.p[0]) : -1;   // original index -> sorted position
+    warp_knn<LPQ>(tgt, active && !resolved, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
+    if (!resolved) { nd = best.d[0]; ni = best.p[0]; }
+    const int pos = ni >= 0 ? __ldg(tgt.inv + ni) : -1;   // original index -> sorted position
     const bool owner = active && (lane & (LPQ - 1)) == 0;
-    const bool valid = owner && pos >= 0 && (double)best.d[0] < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
-    if (owner) corr[j] = valid ? pos : -1;
+    const bool valid = owner && pos >= 0 && (double)nd < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
+    if (owner) corr[j] = valid ? pos : (pos >= 0 ? -2 - pos : -1);
     double acc[kTerms];
 #pragma unroll
     for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
@@ -386,12 +400,17 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
   const dim3 grid(lin_blocks_for(si->n * (lpq >= 4 ? 4 : 1)), 1);
   const unsigned long long seq = ++h->seq;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-#define LAUNCH_LIN(HB, LPQ)                                                                                                              \
-  linearize_kernel<HB, LPQ><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, \
-                                                                 thr2, max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq)
-  if (want_Hb) { if (lpq >= 4) LAUNCH_LIN(true, 4); else LAUNCH_LIN(true, 1); }
-  else { if (lpq >= 4) LAUNCH_LIN(false, 4); else LAUNCH_LIN(false, 1); }
+  // the correspondences of the previous linearize (same clouds, same covariances) seed this one
+  const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
+#define LAUNCH_LIN(HB, LPQ, PREV)                                                                                                        \
+  linearize_kernel<HB, LPQ, PREV><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, \
+                                                                       thr2, max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq)
+#define LAUNCH_LIN_L(HB, PREV) do { if (lpq >= 4) LAUNCH_LIN(HB, 4, PREV); else LAUNCH_LIN(HB, 1, PREV); } while (0)
+  if (want_Hb) { if (use_prev) LAUNCH_LIN_L(true, true); else LAUNCH_LIN_L(true, false); }
+  else { if (use_prev) LAUNCH_LIN_L(false, true); else LAUNCH_LIN_L(false, false); }
+#undef LAUNCH_LIN_L
 #undef LAUNCH_LIN
+  h->corr_n = (size_t)si->n;
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);

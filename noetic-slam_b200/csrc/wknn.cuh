@@ -90,6 +90,62 @@ __device__ __forceinline__ void wknn_stage_chunk(const GridView& g, WarpScratch&
   __syncwarp();
 }
 
+// Exact nearest neighbour when an upper bound is already known (the correspondence of the previous LM iteration,
+// re-measured at the new pose): every point that can beat or tie the bound lies in the closed ball of radius
+// sqrt(d_ub) around the query, which at the level whose cell side is >= the ball's diameter touches at most
+// 2x2x2 cells. The LPQ lanes of the query split those cells and merge with shuffles inside their group.
+// Returns false (nothing searched) when the ball is too large for this shortcut to pay off.
+constexpr int kBallMaxLevelsAboveBase = 2;
+template <int LPQ>
+__device__ __forceinline__ bool ball_search(const GridView& g, float qx, float qy, float qz, int seg, float d_ub, int i_ub,
+                                            float& bd, int& bp) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPQ - 1);
+  const GridMeta* __restrict__ m = g.meta;
+  const float h0 = __ldg(&m->h0), inv_h0 = __ldg(&m->inv_h0), margin = __ldg(&m->margin);
+  const int base = __ldg(&m->base_level);
+  const float4 o = __ldg(g.seg_origin + seg);
+  const float ux = __fsub_rn(qx, o.x), uy = __fsub_rn(qy, o.y), uz = __fsub_rn(qz, o.z);
+  const float r = __fsqrt_ru(d_ub) * 1.000001f + margin;   // covers the fp32 rounding of the metric and of the keys
+  int L = base;
+  float hL = h0 * (float)(1 << base);
+  while (hL < 2.0f * r && L < kTopLevel) { hL *= 2.0f; L++; }
+  if (L > base + kBallMaxLevelsAboveBase) return false;
+  const float inv_hL = inv_h0 / (float)(1 << L);            // powers of two: exact
+  const int maxc = kMaxCoord >> L;
+  const int lox = max((int)floorf((ux - r) * inv_hL), 0), hix = min((int)floorf((ux + r) * inv_hL), maxc);
+  const int loy = max((int)floorf((uy - r) * inv_hL), 0), hiy = min((int)floorf((uy + r) * inv_hL), maxc);
+  const int loz = max((int)floorf((uz - r) * inv_hL), 0), hiz = min((int)floorf((uz + r) * inv_hL), maxc);
+  const int nx = hix - lox + 1, ny = hiy - loy + 1, nz = hiz - loz + 1;
+  if (nx > 2 || ny > 2 || nz > 2) return false;             // cannot happen for hL >= 2r; stay exact if it ever does
+  bd = d_ub;
+  bp = i_ub;
+  const int total = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
+  const unsigned long long sgL = ((unsigned long long)seg << kMortonBits) >> (3 * L);
+  for (int c = sub; c < total; c += LPQ) {
+    const int ix = lox + c % nx, iy = loy + (c / nx) % ny, iz = loz + c / (nx * ny);
+    const unsigned long long ck = ((sgL | morton3((unsigned)ix, (unsigned)iy, (unsigned)iz)) << 4) | (unsigned)L;
+    uint32_t s, e;
+    if (!cell_lookup(g.table, g.table_mask, ck, s, e)) continue;
+    for (uint32_t j = s; j < e; j++) {
+      const float4 p = __ldg(g.pts + j);
+      const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
+      const int pi = __float_as_int(p.w);
+      if (TopK<1>::before(d, pi, bd, bp)) { bd = d; bp = pi; }
+    }
+  }
+  if (LPQ > 1) {
+    const unsigned gmask = ((LPQ == 32) ? 0xffffffffu : ((1u << LPQ) - 1u)) << (lane & ~(LPQ - 1));
+#pragma unroll
+    for (int off = LPQ / 2; off > 0; off >>= 1) {
+      const float od = __shfl_xor_sync(gmask, bd, off);
+      const int op = __shfl_xor_sync(gmask, bp, off);
+      if (TopK<1>::before(od, op, bd, bp)) { bd = od; bp = op; }
+    }
+  }
+  return true;
+}
+
 // LPQ = lanes per query (1, 2, 4 or 8). The LPQ lanes of a query hold identical query state and split the
 // staged candidates between them, which multiplies the number of warps a small cloud can keep in flight
 // (a 65,536-point scan is only 2,048 warps at one query per lane) and shortens every warp's dependent chain.
