@@ -150,6 +150,14 @@ int ngicp_transform_source(ngicp_handle* h, const float T[16], void* out_points,
 int ngicp_batch_covariances(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes,
                             const int64_t* seg_offsets, int n_seg, double* out_4x4, float* out_cov6, float* seg_density);
 
+/* Batched registration units (BASELINE config 5 shape): ngicp_set_input_batch makes `which` a cloud of n_seg scans
+ * stored back to back (seg_offsets[n_seg+1]); covariances are then computed per scan by ngicp_compute_covariances.
+ * ngicp_batch_linearize runs correspondence search + fused linearisation for ALL scans in two launches, scan s at pose
+ * T16s[16*s..] against the (single-cloud) target; outputs are per scan (H36s n_seg x 36, b6s n_seg x 6, errs, ncorrs). */
+int ngicp_set_input_batch(ngicp_handle* h, int which, const void* points, size_t n, size_t stride_bytes,
+                          const int64_t* seg_offsets, int n_seg);
+int ngicp_batch_linearize(ngicp_handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs);
+
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
 typedef struct ngicp_timings {
   float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */
@@ -160,6 +168,7 @@ typedef struct ngicp_timings {
   int linearize_calls;
   int error_calls;
   int kernel_launches;  /* kernels launched by this handle since the last reset */
+  float correspond_ms;  /* K4a: correspondence search launches of the align (linearize_ms holds K4b, the fused linearisation) */
 } ngicp_timings;
 int ngicp_enable_timing(ngicp_handle* h, int on);
 int ngicp_get_timings(ngicp_handle* h, ngicp_timings* out, int reset);

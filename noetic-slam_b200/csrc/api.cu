@@ -223,6 +223,7 @@ int ngicp_create(int device, ngicp_handle** out) {
   CREATE_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->slot_dev), h->slot_host, 0));
   CREATE_CUDA(cudaEventCreate(&h->ev[0]));
   CREATE_CUDA(cudaEventCreate(&h->ev[1]));
+  CREATE_CUDA(cudaEventCreate(&h->ev[2]));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->stage_done, cudaEventDisableTiming));
 #undef CREATE_CUDA
   *out = p;
@@ -248,6 +249,7 @@ int ngicp_destroy(ngicp_handle* p) {
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
   if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  if (h->ev[2]) cudaEventDestroy(h->ev[2]);
   if (h->stage_done) cudaEventDestroy(h->stage_done);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete p;
@@ -710,6 +712,27 @@ int ngicp_batch_covariances(ngicp_handle* p, const void* points, size_t n, size_
   dev_free(d_nbr, st); dev_free(d_dens, st); dev_free(d_sum, st); dev_free(d_cov, st);
   release_index(h, idx);
   return rc;
+}
+
+int ngicp_set_input_batch(ngicp_handle* p, int which, const void* points, size_t n, size_t stride_bytes, const int64_t* seg_offsets, int n_seg) {
+  if (!p || (which != 0 && which != 1) || !seg_offsets) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_input_batch: bad argument");
+  Handle* h = H(p);
+  if (!points || n == 0 || n_seg < 1) return fail(h, NGICP_ERR_INVALID, "ngicp_set_input_batch: empty cloud");
+  if (int rc = use_device(h)) return rc;
+  float* d_xyz = nullptr;
+  if (int rc = upload_xyz(h, points, n, stride_bytes, &d_xyz)) return rc;
+  Index* idx = nullptr;
+  const int rc = build_index(h, d_xyz, 3, (int)n, seg_offsets, n_seg, &idx);
+  dev_free(d_xyz, h->stream);
+  if (rc) return rc;
+  return swap_in_index(h, which, idx);
+}
+
+int ngicp_batch_linearize(ngicp_handle* p, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs) {
+  if (!p || !T16s) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_batch_linearize: NULL argument");
+  Handle* h = H(p);
+  if (int rc = use_device(h)) return rc;
+  return batch_linearize_device(h, n_scans, T16s, H36s, b6s, errs, ncorrs);
 }
 
 // ------------------------------------------------------------------------- timing hooks

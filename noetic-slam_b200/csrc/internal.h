@@ -87,7 +87,7 @@ struct ngicp_handle {
   // timing
   bool timing = false;
   ngicp_timings t;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   std::string err;
 };
 
@@ -126,6 +126,7 @@ int cov6_from_host_order(Handle* h, const Index* idx, const float* d_in6, float*
 // K4 / K5
 int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], double b[6], double* err, int* ncorr);
 int compute_error_device(Handle* h, const double T[16], double* err);
+int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs);
 int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr);
 int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out);
 

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
   int seg = 0;
   if (active) { q = __ldg(g.pts + j); seg = find_segment(g.seg_start, g.n_seg, j); }
   TopK<K> best;
-  warp_knn<LPQ>(g, active, q.x, q.y, q.z, seg, k, cmax, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5]);
+  uint32_t phase = wknn_init(scratch[threadIdx.x >> 5]);
+  warp_knn<LPQ>(g, active, q.x, q.y, q.z, seg, k, cmax, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5], phase);
   if (!active || (threadIdx.x & (LPQ - 1)) != 0) return;
   int* row = nbr + (size_t)j * k;
   if (k == K && (K % 4) == 0) {

@@ -135,27 +135,27 @@ __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* _
   return poses[blockIdx.y];
 }
 
-// K4. grid = (blocks per scan, scans). Source scan b = source segment b; its target segment is
-// target_seg[b] (or 0).
-template <bool WANT_HB, int LPQ, bool USE_PREV>
-__global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
-                                                                 PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ target_seg,
-                                                                 double thr2, float max_sqd, int cmax, int* __restrict__ corr,
-                                                                 double* __restrict__ partials, unsigned int* __restrict__ counters,
-                                                                 ReduceSlot* __restrict__ slots, unsigned long long seq) {
+// K4a. Correspondence search (nano_gicp.cc:219-227): fp32 transform of every source point, exact 1-NN in the target
+// index, strict distance gate. grid = (blocks per scan, scans); source scan b = source segment b, its target segment is
+// target_seg[b] (or 0). Warps are persistent and take work items (32/LPQ consecutive points) round-robin, which
+// spreads the spatially clustered expensive items over the whole grid without giving up a fixed assignment.
+// corr[j] = target sorted position, or -2-pos for a neighbour that failed the gate (kept as a hint for the next
+// iteration), or -1.
+template <int LPQ, bool USE_PREV>
+__global__ void __launch_bounds__(kLinThreads) correspond_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
+                                                                  const int* __restrict__ target_seg, double thr2, float max_sqd, int cmax,
+                                                                  int* __restrict__ corr) {
   const PoseArg P = load_pose(pose0, poses);
   const int b = blockIdx.y;
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
   const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
   const int tseg = target_seg ? __ldg(target_seg + b) : 0;
   __shared__ WarpScratch scratch[kLinThreads / 32];
-  __shared__ double wsum[kLinThreads / 32][kTerms];   // per-warp running sums: keeps 58 registers free during the search
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < kTerms) wsum[warp][lane] = 0.0;
-  __syncwarp();
-  // warp-uniform trip count: the whole warp runs the cooperative search together (wknn.cuh)
-  // LPQ lanes share one source point during the search; lane 0 of the group does the point's arithmetic
-  for (int j0 = begin + (blockIdx.x * kLinThreads + warp * 32) / LPQ; j0 < end; j0 += gridDim.x * kLinThreads / LPQ) {
+  constexpr int kPer = 32 / LPQ;                      // points per work item
+  const int gwarp = blockIdx.x * (kLinThreads / 32) + warp, nwarps = gridDim.x * (kLinThreads / 32);
+  uint32_t phase = wknn_init(scratch[warp]);
+  for (int j0 = begin + gwarp * kPer; j0 < end; j0 += nwarps * kPer) {   // warp-uniform: the whole warp searches together
     const int j = j0 + lane / LPQ;
     const bool active = j < end;
     const float4 pa = active ? __ldg(src.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -171,23 +171,44 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
     int ni = -1;
     if (USE_PREV && active) {
       const int c = corr[j];
-      const int prev = c >= 0 ? c : (c <= -2 ? -2 - c : -1);   // gated-out neighbours are remembered as -2-pos
+      const int prev = c >= 0 ? c : (c <= -2 ? -2 - c : -1);
       if (prev >= 0) {
         const float4 pb0 = __ldg(tgt.pts + prev);
         resolved = ball_search<LPQ>(tgt, qf[0], qf[1], qf[2], tseg, sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z), __float_as_int(pb0.w), nd, ni);
       }
     }
     TopK<1> best;
-    warp_knn<LPQ>(tgt, active && !resolved, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp]);
+    warp_knn<LPQ>(tgt, active && !resolved, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp], phase);
     if (!resolved) { nd = best.d[0]; ni = best.p[0]; }
-    const int pos = ni >= 0 ? __ldg(tgt.inv + ni) : -1;   // original index -> sorted position
-    const bool owner = active && (lane & (LPQ - 1)) == 0;
-    const bool valid = owner && pos >= 0 && (double)nd < thr2;  // strict, float promoted to double (nano_gicp.cc:227)
-    if (owner) corr[j] = valid ? pos : (pos >= 0 ? -2 - pos : -1);
-    double acc[kTerms];
+    if (active && (lane & (LPQ - 1)) == 0) {
+      const int pos = ni >= 0 ? __ldg(tgt.inv + ni) : -1;                 // original index -> sorted position
+      const bool valid = pos >= 0 && (double)nd < thr2;                   // strict, float promoted to double (nano_gicp.cc:227)
+      corr[j] = valid ? pos : (pos >= 0 ? -2 - pos : -1);
+    }
+  }
+}
+
+// K4b. Fused linearisation (nano_gicp.cc:237-241,259-299): per matched source point the Mahalanobis matrix
+// (C_B + R C_A R^T)^-1, the residual, the 6-DoF Jacobian and the 21 + 6 + 1 (+ count) contributions, accumulated in
+// fp64 registers, reduced by warp shuffles, per block, and by the last block to finish (fixed order, compensated).
+// A streaming kernel: 16 B p_A + 24 B C_A + 4 B corr + gathers of 16 B p_B + 24 B C_B per point, nothing written per point.
+template <bool WANT_HB>
+__global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
+                                                                 PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ corr,
+                                                                 double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                                                 ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  const PoseArg P = load_pose(pose0, poses);
+  const int b = blockIdx.y;
+  const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
+  const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
+  __shared__ double wsum[kLinThreads / 32][kTerms];
+  double acc[kTerms];
 #pragma unroll
-    for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
-    if (valid) {
+  for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
+  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
+    const int pos = __ldg(corr + j);
+    if (pos < 0) continue;
+    const float4 pa = __ldg(src.pts + j);
     const float4 pb = __ldg(tgt.pts + pos);
     float ca[6], cb[6];
     {
@@ -210,8 +231,7 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
       cross3(q, M[0], M[1], M[2], g0);
       cross3(q, M[1], M[3], M[4], g1);
       cross3(q, M[2], M[4], M[5], g2);
-      // rows of G: G[i][k] = gk[i]
-      double h0[3], h1[3], h2[3];
+      double h0[3], h1[3], h2[3];   // rows of G: G[i][k] = gk[i]
       cross3(q, g0[0], g1[0], g2[0], h0);
       cross3(q, g0[1], g1[1], g2[1], h1);
       cross3(q, g0[2], g1[2], g2[2], h2);
@@ -222,23 +242,19 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
       acc[15] += M[0]; acc[16] += M[1]; acc[17] += M[2];
       acc[18] += M[3]; acc[19] += M[4];
       acc[20] += M[5];
-      // b = J^T M e = [ -q x Me ; -Me ]
-      double qm[3];
+      double qm[3];   // b = J^T M e = [ -q x Me ; -Me ]
       cross3(q, Me[0], Me[1], Me[2], qm);
       acc[21] -= qm[0]; acc[22] -= qm[1]; acc[23] -= qm[2];
       acc[24] -= Me[0]; acc[25] -= Me[1]; acc[26] -= Me[2];
     }
-    }
-    // only the owner lanes (every LPQ-th) carry values: reduce across them, lane 0 banks the warp's sum
-    if (__any_sync(0xffffffffu, valid)) {
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-      for (int t = 0; t < kTerms; t++) {
-        double v = acc[t];
+  for (int t = 0; t < kTerms; t++) {
+    double v = acc[t];
 #pragma unroll
-        for (int off = 16; off >= LPQ; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) wsum[warp][t] += v;
-      }
-    }
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) wsum[warp][t] = v;
   }
   block_publish<kTerms>(wsum, partials, counters, slots, seq);
 }
@@ -387,42 +403,59 @@ static int ensure_corr(Handle* h, size_t n) {
   return NGICP_OK;
 }
 
-int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
-  if (int rc = check_ready(h)) return rc;
+// search grid: persistent warps, enough of them to fill the machine several times over
+static int search_blocks_for(int n, int lpq) {
+  const int items = (n * lpq + 31) / 32;                         // one warp-sized work item per 32/lpq points
+  const int want = (items + (kLinThreads / 32) - 1) / (kLinThreads / 32);
+  return std::max(1, std::min(want, 148 * 6));
+}
+
+// K4 = correspondence search + fused linearisation over n_scans source segments (n_scans = 1: the reference's
+// linearize). Poses, target segments and per-scan results live in device / host-mapped arrays when batched.
+static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const PoseArg* d_poses, const int* d_target_seg, bool want_Hb,
+                            double* partials, unsigned long long seq) {
   const Index* si = h->index[0];
   const Index* ti = h->index[1];
-  if (si->n_seg != 1 || ti->n_seg != 1) return fail(h, NGICP_ERR_UNSUPPORTED, "linearize: use the batch API for multi-segment clouds");
-  if (int rc = ensure_corr(h, si->n)) return rc;
-  const PoseArg P = make_pose(T);
   const double thr = h->params.max_corr_dist;
   const double thr2 = thr * thr;
   const int lpq = h->k4_lpq > 0 ? h->k4_lpq : 4;
-  const dim3 grid(lin_blocks_for(si->n * (lpq >= 4 ? 4 : 1)), 1);
-  const unsigned long long seq = ++h->seq;
-  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-  // the correspondences of the previous linearize (same clouds, same covariances) seed this one
+  const int per_scan = si->n / n_scans + 1;
+  const dim3 sgrid(search_blocks_for(per_scan, lpq >= 4 ? 4 : 1), n_scans);
+  const dim3 lgrid(lin_blocks_for(per_scan), n_scans);
+  // the correspondences of the previous linearize (same clouds) seed this one
   const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
-#define LAUNCH_LIN(HB, LPQ, PREV)                                                                                                        \
-  linearize_kernel<HB, LPQ, PREV><<<grid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P, nullptr, nullptr, \
-                                                                       thr2, max_sqd_for(thr), h->k4_cmax, h->corr, h->partials, h->counter, h->slot_dev, seq)
-#define LAUNCH_LIN_L(HB, PREV) do { if (lpq >= 4) LAUNCH_LIN(HB, 4, PREV); else LAUNCH_LIN(HB, 1, PREV); } while (0)
-  if (want_Hb) { if (use_prev) LAUNCH_LIN_L(true, true); else LAUNCH_LIN_L(true, false); }
-  else { if (use_prev) LAUNCH_LIN_L(false, true); else LAUNCH_LIN_L(false, false); }
-#undef LAUNCH_LIN_L
-#undef LAUNCH_LIN
+  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+#define LAUNCH_CORR(LPQ, PREV)                                                                                                  \
+  correspond_kernel<LPQ, PREV><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, \
+                                                                     max_sqd_for(thr), h->k4_cmax, h->corr)
+  if (lpq >= 4) { if (use_prev) LAUNCH_CORR(4, true); else LAUNCH_CORR(4, false); }
+  else { if (use_prev) LAUNCH_CORR(1, true); else LAUNCH_CORR(1, false); }
+#undef LAUNCH_CORR
+  if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+  if (want_Hb)
+    linearize_kernel<true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
+                                                                h->counter, h->slot_dev, seq);
+  else
+    linearize_kernel<false><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
+                                                                 h->counter, h->slot_dev, seq);
   h->corr_n = (size_t)si->n;
-  count_launch(h);
+  count_launch(h, 2);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);
-  if (int rc = wait_slot(h, 1, seq)) return rc;
+  if (int rc = wait_slot(h, n_scans, seq)) return rc;
   if (h->timing) {
     cudaEventSynchronize(h->ev[1]);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]);
+    h->t.correspond_ms += ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[1]);
     h->t.linearize_ms += ms;
   }
   h->t.linearize_calls++;
-  const double* v = h->slot_host[0].v;
+  return NGICP_OK;
+}
+
+static void unpack_result(const double* v, bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
   if (H && b && want_Hb) {
     int t = 0;
     for (int r = 0; r < 6; r++)
@@ -430,11 +463,60 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
     for (int i = 0; i < 6; i++) b[i] = v[21 + i];
   }
   if (err) *err = v[27];
-  h->num_correspondences = (int)(v[28] + 0.5);
-  if (ncorr) *ncorr = h->num_correspondences;
+  if (ncorr) *ncorr = (int)(v[28] + 0.5);
+}
+
+int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
+  if (int rc = check_ready(h)) return rc;
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  if (si->n_seg != 1 || ti->n_seg != 1) return fail(h, NGICP_ERR_UNSUPPORTED, "linearize: use ngicp_batch_linearize for multi-segment clouds");
+  if (int rc = ensure_corr(h, si->n)) return rc;
+  const PoseArg P = make_pose(T);
+  const unsigned long long seq = ++h->seq;
+  if (int rc = launch_linearize(h, 1, P, nullptr, nullptr, want_Hb, h->partials, seq)) return rc;
+  int nc = 0;
+  unpack_result(h->slot_host[0].v, want_Hb, H, b, err, &nc);
+  h->num_correspondences = nc;
+  if (ncorr) *ncorr = nc;
   for (int i = 0; i < 9; i++) h->lin_pose[i] = P.R[i];
   for (int i = 0; i < 3; i++) h->lin_pose[9 + i] = P.t[i];
   h->lin_valid = true;
+  return NGICP_OK;
+}
+
+// Batched linearize: source = n_scans segments (ngicp_set_input_batch), every scan with its own pose against the
+// (single-segment) target. One search launch and one linearisation launch for all scans; per-scan results.
+int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs) {
+  if (int rc = check_ready(h)) return rc;
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  if (si->n_seg != n_scans) return fail(h, NGICP_ERR_INVALID, "batch linearize: the source must hold one segment per scan");
+  if (ti->n_seg != 1) return fail(h, NGICP_ERR_UNSUPPORTED, "batch linearize: the target must be a single cloud");
+  if (n_scans < 1 || n_scans > kMaxBatch) return fail(h, NGICP_ERR_INVALID, "batch linearize: 1..256 scans");
+  if (int rc = ensure_corr(h, si->n)) return rc;
+  const int per_scan = si->n / n_scans + 1;
+  const size_t need = (size_t)n_scans * lin_blocks_for(per_scan) * 32;
+  if (h->batch_partials_cap < need) {
+    if (h->batch_partials) NGICP_CUDA(h, cudaFree(h->batch_partials));
+    h->batch_partials = nullptr; h->batch_partials_cap = 0;
+    NGICP_CUDA(h, cudaMalloc(&h->batch_partials, sizeof(double) * need));
+    h->batch_partials_cap = need;
+  }
+  std::vector<PoseArg> poses(n_scans);
+  for (int s = 0; s < n_scans; s++) poses[s] = make_pose(T16s + 16 * (size_t)s);
+  PoseArg* d_poses = nullptr;
+  NGICP_CUDA(h, dev_alloc(&d_poses, (size_t)n_scans, h->stream));
+  NGICP_CUDA(h, cudaMemcpyAsync(d_poses, poses.data(), sizeof(PoseArg) * n_scans, cudaMemcpyHostToDevice, h->stream));
+  NGICP_CUDA(h, cudaStreamSynchronize(h->stream));   // poses is a stack-lifetime pageable buffer
+  const unsigned long long seq = ++h->seq;
+  const int rc = launch_linearize(h, n_scans, poses[0], d_poses, nullptr, true, h->batch_partials, seq);
+  dev_free(d_poses, h->stream);
+  if (rc) return rc;
+  for (int s = 0; s < n_scans; s++)
+    unpack_result(h->slot_host[s].v, true, H36s ? H36s + 36 * (size_t)s : nullptr, b6s ? b6s + 6 * (size_t)s : nullptr, errs ? errs + s : nullptr,
+                  ncorrs ? ncorrs + s : nullptr);
+  h->lin_valid = false;   // the single-scan LM state does not apply to a batch
   return NGICP_OK;
 }
 

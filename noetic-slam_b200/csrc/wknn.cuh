@@ -146,12 +146,20 @@ __device__ __forceinline__ bool ball_search(const GridView& g, float qx, float q
   return true;
 }
 
+// Once per warp and kernel, before the first warp_knn: arm the warp's mbarrier. (Initialising an mbarrier twice is
+// undefined, so persistent kernels that search many times keep one barrier and carry its phase parity along.)
+__device__ __forceinline__ uint32_t wknn_init(WarpScratch& ws) {
+  if ((threadIdx.x & 31) == 0) mbar_init(&ws.mbar, 1);
+  __syncwarp();
+  return 0u;   // parity of the phase the next staged chunk completes
+}
+
 // LPQ = lanes per query (1, 2, 4 or 8). The LPQ lanes of a query hold identical query state and split the
 // staged candidates between them, which multiplies the number of warps a small cloud can keep in flight
 // (a 65,536-point scan is only 2,048 warps at one query per lane) and shortens every warp's dependent chain.
 template <int LPQ, class TK>
 __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float qx, float qy, float qz, int seg, int k, int cmax,
-                                         float max_sqd, TK& best, WarpScratch& ws) {
+                                         float max_sqd, TK& best, WarpScratch& ws, uint32_t& phase) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPQ - 1);
@@ -172,9 +180,6 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     if (reach * reach * 0.999999f >= max_sqd) break;
   }
 
-  if (lane == 0) mbar_init(&ws.mbar, 1);
-  __syncwarp();
-  uint32_t phase = 0;   // parity of the mbarrier phase the next staged chunk completes
   int Lmin = base;  // finest group level this lane still accepts
   bool done = !active;
   best.reset();

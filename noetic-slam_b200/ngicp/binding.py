@@ -25,7 +25,7 @@ SYMBOLS = [
     "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_index_keys", "ngicp_set_input", "ngicp_set_input_device",
     "ngicp_attach_index", "ngicp_get_index", "ngicp_swap_source_and_target", "ngicp_clear", "ngicp_compute_covariances",
     "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
-    "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances",
+    "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances", "ngicp_set_input_batch", "ngicp_batch_linearize",
     "ngicp_enable_timing", "ngicp_get_timings",
 ]
 
@@ -38,7 +38,8 @@ class Params(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("index_ms", C.c_float), ("knn_ms", C.c_float), ("covariance_ms", C.c_float), ("linearize_ms", C.c_float),
-                ("error_ms", C.c_float), ("linearize_calls", C.c_int), ("error_calls", C.c_int), ("kernel_launches", C.c_int)]
+                ("error_ms", C.c_float), ("linearize_calls", C.c_int), ("error_calls", C.c_int), ("kernel_launches", C.c_int),
+                ("correspond_ms", C.c_float)]
 
 
 class NgicpError(RuntimeError):
@@ -105,6 +106,8 @@ def lib() -> C.CDLL:
     L.ngicp_align.argtypes = [vp, fp, fp, ip, ip, dp, dp]
     L.ngicp_transform_source.argtypes = [vp, fp, vp, sz, sz]
     L.ngicp_batch_covariances.argtypes = [vp, vp, sz, sz, C.POINTER(C.c_int64), i, dp, fp, fp]
+    L.ngicp_set_input_batch.argtypes = [vp, i, vp, sz, sz, C.POINTER(C.c_int64), i]
+    L.ngicp_batch_linearize.argtypes = [vp, i, dp, dp, dp, dp, ip]
     L.ngicp_enable_timing.argtypes = [vp, i]
     L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
     _lib = L

@@ -295,6 +295,25 @@ class NanoGICP:
             return cov6, m4.transpose(0, 2, 1).copy(), dens
         return cov6, dens
 
+    def setInputSourceBatch(self, points, seg_offsets):
+        """Many scans stored back to back become the source (one segment per scan) — batched registration units."""
+        p = _pts(points)
+        so = np.ascontiguousarray(seg_offsets, np.int64)
+        B.check(self._h, self._L.ngicp_set_input_batch(self._h, B.SOURCE, p.ctypes.data, p.shape[0], p.strides[0], _ptr(so, C.c_int64), len(so) - 1))
+        self.source_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.SOURCE), p)
+        self._input = points
+        self._n_scans = len(so) - 1
+
+    def batchLinearize(self, Ts):
+        """linearize for every scan of the batched source at its own pose: (errors (S,), H (S,6,6), b (S,6), ncorr (S,))."""
+        Ts = np.asarray(Ts, np.float64)
+        S_ = Ts.shape[0]
+        t = np.ascontiguousarray(Ts.transpose(0, 2, 1)).reshape(S_, 16)
+        H = np.zeros((S_, 6, 6)); b = np.zeros((S_, 6)); e = np.zeros(S_); nc = np.zeros(S_, np.int32)
+        B.check(self._h, self._L.ngicp_batch_linearize(self._h, S_, _ptr(t, C.c_double), _ptr(H, C.c_double), _ptr(b, C.c_double), _ptr(e, C.c_double),
+                                                       _ptr(nc, C.c_int)))
+        return e, H, b, nc
+
     def enableTiming(self, on=True):
         B.check(self._h, self._L.ngicp_enable_timing(self._h, int(on)))
 

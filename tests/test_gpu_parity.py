@@ -367,3 +367,26 @@ def test_batch_covariances_equal_per_keyframe_results():
         assert np.abs(m4[off[s]:off[s + 1]] - single).max() == 0      # keyframes never interact: identical to the per-scan path
         assert abs(dens[s] - g.source_density_) <= 1e-6 * g.source_density_
     assert np.abs(cov6[:, [0, 1, 2, 3, 4, 5]] - m4[:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]]).max() < 1e-7
+
+
+def test_batch_linearize_equals_per_scan_results():
+    """Batched registration units (BASELINE cfg 5 shape): S scans against one target in two launches give, scan by
+    scan, what the single-scan linearize gives."""
+    a, b, _ = S.scan_pair(12, w=128)
+    sc = synth.Scene(12); rng = np.random.default_rng(3)
+    scans = [synth.voxel_filter(synth.scan(sc, P, rng, w=96)) for P in synth.trajectory(sc, 3, 12)] + [b]
+    Ts = [synth.se3((0.002 * i, -0.01, 0.01 * i), (0.05 * i, -0.02, 0.01)) for i in range(len(scans))]
+    g = S.configure(ngicp.NanoGICP(0))
+    g.setInputTarget(a); g.calculateTargetCovariances()
+    single = []
+    for s_, T in zip(scans, Ts):
+        g.setInputSource(s_); g.calculateSourceCovariances()
+        e, H, bb = g.linearize(T)
+        single.append((e, H.copy(), bb.copy(), g.num_correspondences))
+    off = np.cumsum([0] + [len(s_) for s_ in scans])
+    g.setInputSourceBatch(np.concatenate(scans), off)
+    g.calculateSourceCovariances()
+    e, H, bb, nc = g.batchLinearize(np.stack(Ts))
+    for i, (es, Hs, bs, ns) in enumerate(single):
+        assert nc[i] == ns
+        assert abs(e[i] - es) <= 1e-12 * abs(es) and np.abs(H[i] - Hs).max() <= 1e-12 * np.abs(Hs).max() and np.abs(bb[i] - bs).max() <= 1e-12 * np.abs(bs).max()
