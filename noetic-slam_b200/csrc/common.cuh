@@ -80,8 +80,26 @@ __device__ __forceinline__ int voxel_coord_unclamped(float p, float o, float inv
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// inverse of expand3: every third bit of m, compacted
+__host__ __device__ __forceinline__ unsigned int compact3(unsigned long long m) {
+  unsigned long long x = m & 0x1249249249249249ull;
+  x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+  x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+  x = (x ^ (x >> 8)) & 0x1f0000ff0000ffull;
+  x = (x ^ (x >> 16)) & 0x1f00000000ffffull;
+  x = (x ^ (x >> 32)) & 0x1fffffull;
+  return (unsigned int)x;
+}
+// Hash key of a cell: plain packed level-L coordinates (no bit interleaving on the query side — the searches
+// probe dozens of cells per pass and Morton expansion was 40% of their instructions). The sort key stays Morton.
+__device__ __forceinline__ unsigned long long pack_cell(unsigned int seg, int level, unsigned int cx, unsigned int cy, unsigned int cz) {
+  return ((((unsigned long long)seg << 36) | ((unsigned long long)cz << 24) | ((unsigned long long)cy << 12) | (unsigned long long)cx) << 4) |
+         (unsigned long long)level;
+}
+// the same key from a sorted (segment, Morton) key — used by the build, once per cell
 __device__ __forceinline__ unsigned long long cell_key(unsigned long long seg_morton, int level) {
-  return ((seg_morton >> (3 * level)) << 4) | (unsigned long long)level;
+  const unsigned long long m = seg_morton & ((1ull << kMortonBits) - 1ull);
+  return pack_cell((unsigned int)(seg_morton >> kMortonBits), level, compact3(m) >> level, compact3(m >> 1) >> level, compact3(m >> 2) >> level);
 }
 __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
@@ -226,8 +244,6 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
   const int c0x = voxel_coord_unclamped(qx, o.x, inv_h0);
   const int c0y = voxel_coord_unclamped(qy, o.y, inv_h0);
   const int c0z = voxel_coord_unclamped(qz, o.z, inv_h0);
-  const unsigned long long segbits = (unsigned long long)seg << kMortonBits;
-
   int L = base;
   // 1. start level from own-cell occupancy
   for (; L < kTopLevel; L++) {
@@ -237,7 +253,7 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
     const int maxc = kMaxCoord >> L;
     const unsigned int cx = clampi(c0x >> L, 0, maxc), cy = clampi(c0y >> L, 0, maxc), cz = clampi(c0z >> L, 0, maxc);
     uint32_t s, e;
-    const unsigned long long ck = (((segbits >> (3 * L)) | morton3(cx, cy, cz)) << 4) | (unsigned)L;
+    const unsigned long long ck = pack_cell((unsigned)seg, L, cx, cy, cz);
     if (cell_lookup(g.table, g.table_mask, ck, s, e) && (int)(e - s) >= start_count) break;
   }
 
@@ -245,19 +261,16 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
     best.reset();
     const int maxc = kMaxCoord >> L;
     const int cx = clampi(c0x >> L, 0, maxc), cy = clampi(c0y >> L, 0, maxc), cz = clampi(c0z >> L, 0, maxc);
-    const unsigned long long segL = segbits >> (3 * L);
 #pragma unroll 1
     for (int az = cz - 1; az <= cz + 1; az++) {
       if (az < 0 || az > maxc) continue;
-      const unsigned long long kz = segL | (expand3((unsigned)az) << 2);
 #pragma unroll 1
       for (int ay = cy - 1; ay <= cy + 1; ay++) {
         if (ay < 0 || ay > maxc) continue;
-        const unsigned long long kzy = kz | (expand3((unsigned)ay) << 1);
 #pragma unroll 1
         for (int ax = cx - 1; ax <= cx + 1; ax++) {
           if (ax < 0 || ax > maxc) continue;
-          const unsigned long long ck = ((kzy | expand3((unsigned)ax)) << 4) | (unsigned)L;
+          const unsigned long long ck = pack_cell((unsigned)seg, L, (unsigned)ax, (unsigned)ay, (unsigned)az);
           uint32_t s, e;
           if (!cell_lookup(g.table, g.table_mask, ck, s, e)) continue;
           for (uint32_t j = s; j < e; j++) {

@@ -12,6 +12,8 @@
 // solve waits on a sequence number, not on a stream synchronise.
 // compute_error does not cache the Mahalanobis matrices: it rebuilds them from the pose of the last
 // linearize with the very same device function, so both kernels see bit-identical M.
+#include <cstdlib>
+
 #include "internal.h"
 #include "linearize.cuh"
 #include "wknn.cuh"
@@ -19,6 +21,11 @@
 namespace ngicp {
 
 namespace {
+
+#ifdef NGICP_STATS
+__device__ unsigned long long g_lin_hist[32];
+__device__ unsigned int g_item_cycles[1 << 16];   // per work item: cycles of the search   // [0..15] per-item cycles (log2 buckets from 2^10), [16..31] per-warp totals
+#endif
 
 constexpr int kTerms = 29;  // 21 H + 6 b + error + count(c>0)
 constexpr int kLinThreads = 128;
@@ -155,7 +162,13 @@ __global__ void __launch_bounds__(kLinThreads) correspond_kernel(GridView src, G
   constexpr int kPer = 32 / LPQ;                      // points per work item
   const int gwarp = blockIdx.x * (kLinThreads / 32) + warp, nwarps = gridDim.x * (kLinThreads / 32);
   uint32_t phase = wknn_init(scratch[warp]);
+#ifdef NGICP_STATS
+  const long long t_warp0 = clock64();
+#endif
   for (int j0 = begin + gwarp * kPer; j0 < end; j0 += nwarps * kPer) {   // warp-uniform: the whole warp searches together
+#ifdef NGICP_STATS
+    const long long t_item0 = clock64();
+#endif
     const int j = j0 + lane / LPQ;
     const bool active = j < end;
     const float4 pa = active ? __ldg(src.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -185,7 +198,13 @@ __global__ void __launch_bounds__(kLinThreads) correspond_kernel(GridView src, G
       const bool valid = pos >= 0 && (double)nd < thr2;                   // strict, float promoted to double (nano_gicp.cc:227)
       corr[j] = valid ? pos : (pos >= 0 ? -2 - pos : -1);
     }
+#ifdef NGICP_STATS
+    if (lane == 0) { const long long dt = clock64() - t_item0; g_item_cycles[((j0 - begin) / kPer) & 0xffff] = (unsigned int)dt; int bkt = 0; while ((1ll << (bkt + 10)) < dt && bkt < 15) bkt++; atomicAdd(&g_lin_hist[bkt], 1ull); }
+#endif
   }
+#ifdef NGICP_STATS
+  if (lane == 0) { const long long dt = clock64() - t_warp0; int bkt = 0; while ((1ll << (bkt + 10)) < dt && bkt < 15) bkt++; atomicAdd(&g_lin_hist[16 + bkt], 1ull); }
+#endif
 }
 
 // K4b. Fused linearisation (nano_gicp.cc:237-241,259-299): per matched source point the Mahalanobis matrix
@@ -362,7 +381,10 @@ static float max_sqd_for(double thr) {
   return __builtin_nextafterf(f, __builtin_inff());
 }
 
+static int g_lin_block_cap = -1;
 int lin_blocks_for(int n) {
+  if (g_lin_block_cap < 0) { const char* e = std::getenv("NGICP_LIN_BLOCKS"); g_lin_block_cap = e ? std::atoi(e) : 0; }
+  if (g_lin_block_cap > 0) return std::max(1, std::min((n + kLinThreads - 1) / kLinThreads, g_lin_block_cap));
   const int want = (n + kLinThreads - 1) / kLinThreads;  // one search lane-group per thread slot: latency-bound, spread it wide
   return std::max(1, std::min(want, kMaxLinBlocks));
 }
@@ -589,6 +611,23 @@ extern "C" int ngicp_debug_stats_lin(unsigned long long out[8], int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, ngicp::g_wknn_stats, sizeof(unsigned long long) * 8);
   if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ngicp::g_wknn_stats, z, sizeof z); }
+  return 0;
+}
+#endif
+
+#ifdef NGICP_STATS
+extern "C" int ngicp_debug_lin_hist(unsigned long long out[32], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_lin_hist, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(ngicp::g_lin_hist, z, sizeof z); }
+  return 0;
+}
+#endif
+
+#ifdef NGICP_STATS
+extern "C" int ngicp_debug_item_cycles(unsigned int* out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_item_cycles, sizeof(unsigned int) * n);
   return 0;
 }
 #endif

@@ -32,11 +32,12 @@ static __device__ unsigned long long g_wknn_stats[8];
 #endif
 
 struct __align__(16) WarpScratch {
-  float4 pts[kWarpChunk];       // staged candidates (written by the TMA bulk copies)
+  float4 pts[2][kWarpChunk];    // staged candidates, double buffered (written by the TMA bulk copies)
   uint32_t rstart[64];          // non-empty voxel buckets of the block, compacted, in scan order
   uint32_t rpre[65];            // exclusive prefix of their sizes; rpre[R] = M
   uint32_t pad;
-  unsigned long long mbar;      // mbarrier the bulk copies complete on (one per warp)
+  unsigned long long mbar[2];   // one mbarrier per buffer: the bulk copies complete on it
+  float4 qm[8];                 // member queries of the current pass (k = 1 path)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,36 +60,43 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-// block cells in scan order: the 8 children of the group cell first (they hold the nearest candidates,
-// so the top-k threshold tightens early and later candidates rarely insert), then the surrounding ring.
-// entry = (ox+1) | (oy+1)<<2 | (oz+1)<<4 with offsets o in [-1,2] relative to the group cell's first child.
-__device__ __constant__ unsigned char kBlockOrder[64] = {
-    0x15, 0x16, 0x19, 0x1a, 0x25, 0x26, 0x29, 0x2a,
-    0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x06, 0x07, 0x08, 0x09, 0x0a, 0x0b, 0x0c, 0x0d, 0x0e, 0x0f,
-    0x10, 0x11, 0x12, 0x13, 0x14, 0x17, 0x18, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f,
-    0x20, 0x21, 0x22, 0x23, 0x24, 0x27, 0x28, 0x2b, 0x2c, 0x2d, 0x2e, 0x2f,
-    0x30, 0x31, 0x32, 0x33, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x3b, 0x3c, 0x3d, 0x3e, 0x3f};
-
-// Stage candidates [c0, c0+nch) of the concatenated bucket list into shared memory. Every voxel bucket is a
-// contiguous run of float4 in the Morton-sorted array, so each overlapping bucket is ONE TMA bulk copy
-// (cp.async.bulk, issued by the lane that owns the bucket), then the warp waits on the mbarrier. The original
-// index of every candidate rides in the .w lane of the copied float4.
-__device__ __forceinline__ void wknn_stage_chunk(const GridView& g, WarpScratch& ws, int lane, int R, uint32_t c0, int nch, uint32_t& phase) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the previous chunk before async writes
-  if (lane == 0) mbar_expect_tx(&ws.mbar, (uint32_t)nch * 16u);
+// Stage candidates [c0, c0+nch) of the concatenated bucket list into shared-memory buffer `buf`. Every voxel bucket
+// is a contiguous run of float4 in the Morton-sorted array, so each overlapping bucket is ONE TMA bulk copy
+// (cp.async.bulk, issued by the lane that owns the bucket) completing on the buffer's mbarrier. The original index of
+// every candidate rides in the .w lane of the copied float4. Issue and wait are separate so that the next chunk
+// streams in while the warp scans the current one.
+__device__ __forceinline__ void wknn_issue(const GridView& g, WarpScratch& ws, int buf, int lane, int R, uint32_t c0, int nch) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this buffer before async writes
+  if (lane == 0) mbar_expect_tx(&ws.mbar[buf], (uint32_t)nch * 16u);
   const uint32_t c1 = c0 + (uint32_t)nch;
   for (int ri = lane; ri < R; ri += 32) {
     const uint32_t pre = ws.rpre[ri], nxt = ws.rpre[ri + 1];
     const uint32_t lo = max(pre, c0), hi = min(nxt, c1);
-    if (lo < hi) tma_bulk_g2s(&ws.pts[lo - c0], g.pts + (ws.rstart[ri] + (lo - pre)), (hi - lo) * 16u, &ws.mbar);
+    if (lo < hi) tma_bulk_g2s(&ws.pts[buf][lo - c0], g.pts + (ws.rstart[ri] + (lo - pre)), (hi - lo) * 16u, &ws.mbar[buf]);
   }
+}
+__device__ __forceinline__ void wknn_wait(WarpScratch& ws, int buf, uint32_t& phase) {
   unsigned int spins = 0;
-  while (!mbar_try_wait(&ws.mbar, phase)) {
+  while (!mbar_try_wait(&ws.mbar[buf], (phase >> buf) & 1u)) {
     if (++spins > (1u << 24)) __trap();   // never hang the GPU on a programming error
   }
-  phase ^= 1u;
+  phase ^= 1u << buf;
   __syncwarp();
 }
+// chunk loop used by every scan mode: prefetch chunk c+1, wait for chunk c, run BODY(P, nch) on it
+#define WKNN_FOR_CHUNKS(...)                                                                               \
+  {                                                                                                        \
+    int buf_ = 0;                                                                                          \
+    if (M > 0) wknn_issue(g, ws, 0, lane, R, 0u, (int)min((uint32_t)kWarpChunk, M));                       \
+    for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk, buf_ ^= 1) {                                           \
+      const int nch = (int)min((uint32_t)kWarpChunk, M - c0);                                              \
+      if (c0 + kWarpChunk < M) wknn_issue(g, ws, buf_ ^ 1, lane, R, c0 + kWarpChunk, (int)min((uint32_t)kWarpChunk, M - c0 - kWarpChunk)); \
+      wknn_wait(ws, buf_, phase);                                                                          \
+      const float4* __restrict__ P = ws.pts[buf_];                                                         \
+      __VA_ARGS__                                                                                          \
+      __syncwarp();                                                                                        \
+    }                                                                                                      \
+  }
 
 // Exact nearest neighbour when an upper bound is already known (the correspondence of the previous LM iteration,
 // re-measured at the new pose): every point that can beat or tie the bound lies in the closed ball of radius
@@ -121,17 +129,22 @@ __device__ __forceinline__ bool ball_search(const GridView& g, float qx, float q
   bd = d_ub;
   bp = i_ub;
   const int total = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
-  const unsigned long long sgL = ((unsigned long long)seg << kMortonBits) >> (3 * L);
   for (int c = sub; c < total; c += LPQ) {
     const int ix = lox + c % nx, iy = loy + (c / nx) % ny, iz = loz + c / (nx * ny);
-    const unsigned long long ck = ((sgL | morton3((unsigned)ix, (unsigned)iy, (unsigned)iz)) << 4) | (unsigned)L;
+    const unsigned long long ck = pack_cell((unsigned)seg, L, (unsigned)ix, (unsigned)iy, (unsigned)iz);
     uint32_t s, e;
     if (!cell_lookup(g.table, g.table_mask, ck, s, e)) continue;
-    for (uint32_t j = s; j < e; j++) {
-      const float4 p = __ldg(g.pts + j);
-      const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
-      const int pi = __float_as_int(p.w);
-      if (TopK<1>::before(d, pi, bd, bp)) { bd = d; bp = pi; }
+    // four independent loads in flight per step: a serial load->compare chain would pay one memory latency per point
+    for (uint32_t j = s; j < e; j += 4) {
+      float4 p[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) p[t] = __ldg(g.pts + min(j + t, e - 1));
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float d = sqdist_ref(qx, qy, qz, p[t].x, p[t].y, p[t].z);
+        const int pi = __float_as_int(p[t].w);
+        if (TopK<1>::before(d, pi, bd, bp)) { bd = d; bp = pi; }   // re-offering a duplicate of the last point is harmless
+      }
     }
   }
   if (LPQ > 1) {
@@ -149,9 +162,9 @@ __device__ __forceinline__ bool ball_search(const GridView& g, float qx, float q
 // Once per warp and kernel, before the first warp_knn: arm the warp's mbarrier. (Initialising an mbarrier twice is
 // undefined, so persistent kernels that search many times keep one barrier and carry its phase parity along.)
 __device__ __forceinline__ uint32_t wknn_init(WarpScratch& ws) {
-  if ((threadIdx.x & 31) == 0) mbar_init(&ws.mbar, 1);
+  if ((threadIdx.x & 31) == 0) { mbar_init(&ws.mbar[0], 1); mbar_init(&ws.mbar[1], 1); }
   __syncwarp();
-  return 0u;   // parity of the phase the next staged chunk completes
+  return 0u;   // bit b = parity of the phase the next chunk staged into buffer b completes
 }
 
 // LPQ = lanes per query (1, 2, 4 or 8). The LPQ lanes of a query hold identical query state and split the
@@ -192,17 +205,19 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     const int lcx = __shfl_sync(FULL, c0x, leader), lcy = __shfl_sync(FULL, c0y, leader), lcz = __shfl_sync(FULL, c0z, leader);
     const int sg = __shfl_sync(FULL, seg, leader);
     const int lLmin = __shfl_sync(FULL, Lmin, leader);
-    const unsigned long long sgbits = (unsigned long long)sg << kMortonBits;
 
     // ---- 1. group level: largest ancestor of the leader (levels base+1 .. top) with <= cmax points
     int Lg;
-    {
+    if (lLmin > base) {
+      // the leader was refused one level below: go exactly one level up, no need to probe its ancestors again
+      Lg = min(lLmin, kTopLevel);
+    } else {
       const int P = base + 1 + lane;
       bool ok = false;
       if (P <= kTopLevel) {
         const int maxcP = kMaxCoord >> P;
         const unsigned int ax = clampi(lcx >> P, 0, maxcP), ay = clampi(lcy >> P, 0, maxcP), az = clampi(lcz >> P, 0, maxcP);
-        const unsigned long long ck = (((sgbits >> (3 * P)) | morton3(ax, ay, az)) << 4) | (unsigned)P;
+        const unsigned long long ck = pack_cell((unsigned)sg, P, ax, ay, az);
         uint32_t s = 0, e = 0;
         const bool hit = cell_lookup(g.table, g.table_mask, ck, s, e);
         ok = !hit || (int)(e - s) <= cmax;
@@ -210,9 +225,8 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
       const unsigned okm = __ballot_sync(FULL, ok);
       // counts grow with the level, so the ok lanes form a prefix; take its last lane
       const int nprefix = __ffs(~okm) - 1;          // number of leading ok lanes (0..12)
-      Lg = base + (nprefix > 0 ? nprefix - 1 : 0) ;  // group cell level P = Lg + 1
-      Lg = max(Lg, lLmin);
-      Lg = min(Lg, max(L_reach, lLmin));
+      Lg = base + (nprefix > 0 ? nprefix - 1 : 0);  // group cell level P = Lg + 1
+      Lg = min(Lg, L_reach);
       Lg = min(Lg, kTopLevel);
     }
 
@@ -222,20 +236,42 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     const bool member = !done && Lmin <= Lg && seg == sg && px == lpx && py == lpy && pz == lpz;
 
     // ---- 3. 64 hash probes, two per lane; ranges + exclusive prefix of their sizes into shared memory
-    const unsigned long long sgL = sgbits >> (3 * Lg);
     uint32_t cnt[2], st[2];
+    {
+      unsigned long long ck[2];
+      uint32_t hh[2];
+      uint4 raw[2];
+      bool inside[2];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      const int ci = lane + 32 * half;
-      const unsigned code = kBlockOrder[ci];
-      const int ax = 2 * lpx + (int)(code & 3) - 1, ay = 2 * lpy + (int)((code >> 2) & 3) - 1, az = 2 * lpz + (int)((code >> 4) & 3) - 1;
-      uint32_t s = 0, e = 0;
-      if (ax >= 0 && ax <= maxc && ay >= 0 && ay <= maxc && az >= 0 && az <= maxc) {
-        const unsigned long long ck = ((sgL | morton3((unsigned)ax, (unsigned)ay, (unsigned)az)) << 4) | (unsigned)Lg;
-        if (!cell_lookup(g.table, g.table_mask, ck, s, e)) { s = 0; e = 0; }
+      for (int half = 0; half < 2; half++) {
+        // scan order without a table (a lane-indexed __constant__ table serialised 32 ways): bits 5..3 of the cell id say
+        // per axis whether the cell lies in the outer ring, bits 2..0 pick the side. Ids 0..7 are the 8 children of the
+        // group cell (they hold the nearest candidates, so the top-k threshold tightens early), the ring follows.
+        const int ci = lane + 32 * half;
+        const int ox = (ci & 8) ? ((ci & 1) ? 2 : -1) : (ci & 1), oy = (ci & 16) ? ((ci & 2) ? 2 : -1) : ((ci >> 1) & 1),
+                  oz = (ci & 32) ? ((ci & 4) ? 2 : -1) : ((ci >> 2) & 1);
+        const int ax = 2 * lpx + ox, ay = 2 * lpy + oy, az = 2 * lpz + oz;
+        inside[half] = ax >= 0 && ax <= maxc && ay >= 0 && ay <= maxc && az >= 0 && az <= maxc;
+        ck[half] = pack_cell((unsigned)sg, Lg, (unsigned)ax, (unsigned)ay, (unsigned)az);
+        hh[half] = hash64(ck[half]) & g.table_mask;
       }
-      st[half] = s;
-      cnt[half] = e - s;
+      // both first probes are issued before either is consumed (one memory round trip instead of two)
+#pragma unroll
+      for (int half = 0; half < 2; half++) raw[half] = inside[half] ? __ldg(reinterpret_cast<const uint4*>(g.table + hh[half])) : make_uint4(~0u, ~0u, 0u, 0u);
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t s = 0, e = 0;
+        unsigned long long k = ((unsigned long long)raw[half].y << 32) | raw[half].x;
+        uint32_t hcur = hh[half];
+        while (k != kEmptyKey) {
+          if (k == ck[half]) { s = raw[half].z; e = raw[half].w; break; }
+          hcur = (hcur + 1) & g.table_mask;            // collision: continue the probe sequence
+          raw[half] = __ldg(reinterpret_cast<const uint4*>(g.table + hcur));
+          k = ((unsigned long long)raw[half].y << 32) | raw[half].x;
+        }
+        st[half] = s;
+        cnt[half] = e - s;
+      }
     }
     uint32_t inc0 = cnt[0], inc1 = cnt[1];
 #pragma unroll
@@ -267,27 +303,70 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     const unsigned mem_mask = __ballot_sync(FULL, member);
     const int nmem = __popc(mem_mask) / LPQ;
     const unsigned grp_mask = (LPQ == 32 ? 0xffffffffu : ((1u << LPQ) - 1u));
-    if (TK::kK == 1) {
-      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
-        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
+    if (TK::kK == 1 && LPQ >= 4) {
+      // k = 1, at most 8 queries per warp: every lane keeps a running best for each member query over ITS share of the
+      // candidates (8 per staged chunk) and the warp-argmin is taken once per member at the end of the pass, not per
+      // chunk — the heavy tail (thousands of candidates) is no longer paced by shuffle reductions.
+      constexpr int NS = 32 / LPQ;
+      if (member && sub == 0) ws.qm[lane / LPQ] = make_float4(qx, qy, qz, 0.f);
+      unsigned slots = 0;
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) slots |= ((mem_mask >> (sl * LPQ)) & 1u) << sl;
+      __syncwarp();
+      float bd[NS];
+      int bp[NS];
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) { bd[sl] = __int_as_float(0x7f800000); bp[sl] = -1; }
+      WKNN_FOR_CHUNKS({
         float4 cand[kWarpChunk / 32];
 #pragma unroll
-        for (int t = 0; t < kWarpChunk / 32; t++) cand[t] = ws.pts[min(lane + 32 * t, nch - 1)];
+        for (int t = 0; t < kWarpChunk / 32; t++) {
+          cand[t] = P[min(lane + 32 * t, nch - 1)];
+          if (lane + 32 * t >= nch) cand[t].w = __int_as_float(-1);   // padding: loses every comparison below
+        }
+#pragma unroll
+        for (int sl = 0; sl < NS; sl++) {
+          if (!((slots >> sl) & 1u)) continue;
+          const float4 mq = ws.qm[sl];
+#pragma unroll
+          for (int t = 0; t < kWarpChunk / 32; t++) {
+            const float d = sqdist_ref(mq.x, mq.y, mq.z, cand[t].x, cand[t].y, cand[t].z);
+            const int pi = __float_as_int(cand[t].w);
+            if (pi >= 0 && TK::before(d, pi, bd[sl], bp[sl])) { bd[sl] = d; bp[sl] = pi; }
+          }
+        }
+      })
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) {
+        if (!((slots >> sl) & 1u)) continue;
+        float rd = bd[sl];
+        int rp = bp[sl];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const float od = __shfl_xor_sync(FULL, rd, off);
+          const int op = __shfl_xor_sync(FULL, rp, off);
+          if (TK::before(od, op, rd, rp)) { rd = od; rp = op; }
+        }
+        if (lane / LPQ == sl && rp >= 0 && rd <= best.worst()) best.offer(rd, rp);
+      }
+    } else if (TK::kK == 1) {
+      WKNN_FOR_CHUNKS({
+        float4 cand[kWarpChunk / 32];
+#pragma unroll
+        for (int t = 0; t < kWarpChunk / 32; t++) cand[t] = P[min(lane + 32 * t, nch - 1)];
         unsigned rem = mem_mask;
         while (rem) {
           const int mi = __ffs(rem) - 1;                 // first lane of the next member query
           rem &= ~(grp_mask << (mi & ~(LPQ - 1)));
           const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
           float bd = __int_as_float(0x7f800000);
-          int be = -1;
+          int bp = -1;
 #pragma unroll
           for (int t = 0; t < kWarpChunk / 32; t++) {
-            const int e = lane + 32 * t;
             const float d = sqdist_ref(mx, my, mz, cand[t].x, cand[t].y, cand[t].z);
-            if (e < nch && d < bd) { bd = d; be = e; }
+            const int pi = __float_as_int(cand[t].w);
+            if (lane + 32 * t < nch && TK::before(d, pi, bd, bp)) { bd = d; bp = pi; }
           }
-          int bp = be >= 0 ? __float_as_int(ws.pts[be].w) : -1;
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) {
             const float od = __shfl_xor_sync(FULL, bd, off);
@@ -296,8 +375,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           }
           if ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1)) && bp >= 0 && bd <= best.worst()) best.offer(bd, bp);
         }
-        __syncwarp();
-      }
+      })
     } else if ((long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M) {
       // heavy tail: few member queries, many candidates -> all 32 lanes split the candidates of one query
       unsigned rem = mem_mask;
@@ -307,16 +385,13 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
         const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
         TK part;
         part.reset();
-        for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
-          const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-          wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
+        WKNN_FOR_CHUNKS({
           for (int e = lane; e < nch; e += 32) {
-            const float4 p = ws.pts[e];
+            const float4 p = P[e];
             const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
             if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
           }
-          __syncwarp();
-        }
+        })
         const bool mine = (lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1));
 #pragma unroll
         for (int rr = 0; rr < TK::kK; rr++) {   // merge the 32 private lists: K rounds of "smallest head wins"
@@ -333,37 +408,31 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
         }
       }
     } else if (LPQ == 1) {
-      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
-        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
+      WKNN_FOR_CHUNKS({
         if (member) {
 #pragma unroll 4
           for (int e = 0; e < nch; e++) {
-            const float4 p = ws.pts[e];
+            const float4 p = P[e];
             const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
             if (d <= best.worst()) best.offer(d, __float_as_int(p.w));
           }
         }
-        __syncwarp();
-      }
+      })
     } else {
       // shared mode, LPQ lanes per query: lane `sub` takes candidates sub, sub+LPQ, ... into a private list,
       // then the LPQ lists of a query are merged by K rounds of group-argmin (xor shuffles inside the group)
       TK part;
       part.reset();
-      for (uint32_t c0 = 0; c0 < M; c0 += kWarpChunk) {
-        const int nch = (int)min((uint32_t)kWarpChunk, M - c0);
-        wknn_stage_chunk(g, ws, lane, R, c0, nch, phase);
+      WKNN_FOR_CHUNKS({
         if (member) {
 #pragma unroll 2
           for (int e = sub; e < nch; e += LPQ) {
-            const float4 p = ws.pts[e];
+            const float4 p = P[e];
             const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
             if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
           }
         }
-        __syncwarp();
-      }
+      })
 #pragma unroll
       for (int rr = 0; rr < TK::kK; rr++) {
         float gd = part.d[0];
