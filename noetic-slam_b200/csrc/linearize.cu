@@ -443,7 +443,8 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   const int lpq = h->k4_lpq > 0 ? h->k4_lpq : 4;
   const int per_scan = si->n / n_scans + 1;
   const dim3 sgrid(search_blocks_for(per_scan, lpq >= 4 ? 4 : 1), n_scans);
-  const dim3 lgrid(lin_blocks_for(per_scan), n_scans);
+  // batched: few fat blocks per scan (many points per thread amortise the 29-term block reduction); single scan: wide
+  const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * 8) / n_scans)), n_scans);
   // the correspondences of the previous linearize (same clouds) seed this one
   const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
@@ -518,7 +519,7 @@ int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H
   if (n_scans < 1 || n_scans > kMaxBatch) return fail(h, NGICP_ERR_INVALID, "batch linearize: 1..256 scans");
   if (int rc = ensure_corr(h, si->n)) return rc;
   const int per_scan = si->n / n_scans + 1;
-  const size_t need = (size_t)n_scans * lin_blocks_for(per_scan) * 32;
+  const size_t need = (size_t)n_scans * lin_blocks_for(per_scan) * 32;   // upper bound on blocks per scan
   if (h->batch_partials_cap < need) {
     if (h->batch_partials) NGICP_CUDA(h, cudaFree(h->batch_partials));
     h->batch_partials = nullptr; h->batch_partials_cap = 0;
