@@ -158,6 +158,23 @@ int ngicp_set_input_batch(ngicp_handle* h, int which, const void* points, size_t
                           const int64_t* seg_offsets, int n_seg);
 int ngicp_batch_linearize(ngicp_handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs);
 
+/* ---- device-resident keyframe store + submap assembly (additive, not in the reference) -------
+ * Replaces the host round trip DLIO makes for every submap: keyframe cloud + covariance list kept on the host
+ * (odom.cc:1592), transformed there (pcl::transformPointCloud + cov <- Td cov Td^T, odom.cc:1757-1762), concatenated
+ * (odom.cc:1719-1729) and handed back through setInputTarget / setTargetCovariances (odom.cc:1737, :998).
+ *   capture   : snapshot the handle's SOURCE cloud and covariances (already in HBM) as a keyframe, original point order
+ *   transform : in place, points fp32 R p + t, covariances Td C Td^T with Td = T.cast<double>()
+ *   assemble  : concatenate keyframes in the given order into the handle's TARGET cloud, build its index and attach
+ *               the concatenated covariances — no PCIe traffic. */
+typedef struct ngicp_keyframe ngicp_keyframe;
+int ngicp_keyframe_capture(ngicp_handle* h, ngicp_keyframe** out);
+int ngicp_keyframe_transform(ngicp_handle* h, ngicp_keyframe* kf, const float T[16]);
+size_t ngicp_keyframe_size(const ngicp_keyframe* kf);
+int ngicp_keyframe_release(ngicp_handle* h, ngicp_keyframe* kf);
+/* copy a keyframe to the host for inspection: xyz n x 3 floats and/or n x 16 doubles (either may be NULL) */
+int ngicp_keyframe_download(ngicp_handle* h, const ngicp_keyframe* kf, float* xyz, double* cov_4x4);
+int ngicp_submap_assemble(ngicp_handle* h, ngicp_keyframe* const* kfs, int n_kfs);
+
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
 typedef struct ngicp_timings {
   float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */

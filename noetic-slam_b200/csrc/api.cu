@@ -415,7 +415,9 @@ ngicp_index* ngicp_get_index(ngicp_handle* p, int which) {
   return wrap(H(p)->index[which]);
 }
 
-static int swap_in_index(Handle* h, int which, Index* idx) {
+extern "C++" {
+namespace ngicp {
+int swap_in_index(Handle* h, int which, Index* idx) {
   // same stream as everything else this handle does: no synchronisation needed to swap
   Index* old = h->index[which];
   h->index[which] = idx;
@@ -427,6 +429,9 @@ static int swap_in_index(Handle* h, int which, Index* idx) {
   h->lin_valid = false;
   return NGICP_OK;
 }
+int select_device(Handle* h) { return use_device(h); }
+}  // namespace ngicp
+}  // extern "C++"
 
 int ngicp_set_input(ngicp_handle* p, int which, const void* points, size_t n, size_t stride_bytes) {
   if (!p || (which != 0 && which != 1)) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_input: bad argument");

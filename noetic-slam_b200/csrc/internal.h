@@ -130,6 +130,10 @@ int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H
 int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr);
 int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out);
 
+// bookkeeping shared with keyframe.cu
+int swap_in_index(Handle* h, int which, Index* idx);   // make idx the source/target cloud, drop that side's covariances
+int select_device(Handle* h);
+
 // workspace helpers (stream-ordered pool)
 template <typename T>
 inline cudaError_t dev_alloc(T** p, size_t count, cudaStream_t s) {

@@ -114,26 +114,50 @@ __device__ __forceinline__ void block_publish(double (*sm)[NT], double* __restri
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // Lane t folds term t over the block partials i = warp, warp + kWarps, ... (fixed order, Neumaier); eight
+  // independent loads are in flight per step because this tail is pure L2 latency. The four per-warp sums are folded
+  // in warp order, written to the host-mapped slot as one row, and published with a single system fence.
+  __shared__ double fin[kWarps][2][32];
   const double* all = partials + (size_t)b * gridDim.x * 32;
-  for (int t = warp; t < NT; t += kWarps) {
-    double s = 0.0, c = 0.0;  // Neumaier
-    for (unsigned int i = lane; i < gridDim.x; i += 32) {
-      const double x = __ldcg(all + (size_t)i * 32 + t);
-      const double y = s + x;
-      c += (fabs(s) >= fabs(x)) ? ((s - y) + x) : ((x - y) + s);
-      s = y;
-    }
-    double v = s + c;
+  const unsigned int nb = gridDim.x;
+  double s = 0.0, c = 0.0;
+  if (lane < NT) {
+    for (unsigned int i0 = warp; i0 < nb; i0 += kWarps * 8) {
+      double x[8];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) { slots[b].v[t] = v; __threadfence_system(); }
+      for (int u = 0; u < 8; u++) {
+        const unsigned int i = i0 + u * kWarps;
+        x[u] = i < nb ? __ldcg(all + (size_t)i * 32 + lane) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double y = s + x[u];
+        c += (fabs(s) >= fabs(x[u])) ? ((s - y) + x[u]) : ((x[u] - y) + s);
+        s = y;
+      }
+    }
   }
+  fin[warp][0][lane] = s;
+  fin[warp][1][lane] = c;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp != 0) return;
+  if (lane < NT) {
+    double ts = 0.0, tc = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+      const double x = fin[w][0][lane];
+      const double y = ts + x;
+      tc += (fabs(ts) >= fabs(x)) ? ((ts - y) + x) : ((x - y) + ts);
+      ts = y;
+      tc += fin[w][1][lane];
+    }
+    slots[b].v[lane] = ts + tc;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
     counters[b] = 0;  // ready for the next launch
-    __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&slots[b].seq) = seq;
-    __threadfence_system();
   }
 }
 

@@ -26,6 +26,8 @@ SYMBOLS = [
     "ngicp_attach_index", "ngicp_get_index", "ngicp_swap_source_and_target", "ngicp_clear", "ngicp_compute_covariances",
     "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
     "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances", "ngicp_set_input_batch", "ngicp_batch_linearize",
+    "ngicp_keyframe_capture", "ngicp_keyframe_transform", "ngicp_keyframe_size", "ngicp_keyframe_release", "ngicp_keyframe_download",
+    "ngicp_submap_assemble",
     "ngicp_enable_timing", "ngicp_get_timings",
 ]
 
@@ -108,6 +110,13 @@ def lib() -> C.CDLL:
     L.ngicp_batch_covariances.argtypes = [vp, vp, sz, sz, C.POINTER(C.c_int64), i, dp, fp, fp]
     L.ngicp_set_input_batch.argtypes = [vp, i, vp, sz, sz, C.POINTER(C.c_int64), i]
     L.ngicp_batch_linearize.argtypes = [vp, i, dp, dp, dp, dp, ip]
+    L.ngicp_keyframe_capture.argtypes = [vp, C.POINTER(vp)]
+    L.ngicp_keyframe_transform.argtypes = [vp, vp, fp]
+    L.ngicp_keyframe_size.restype = sz
+    L.ngicp_keyframe_size.argtypes = [vp]
+    L.ngicp_keyframe_release.argtypes = [vp, vp]
+    L.ngicp_keyframe_download.argtypes = [vp, vp, fp, dp]
+    L.ngicp_submap_assemble.argtypes = [vp, C.POINTER(vp), i]
     L.ngicp_enable_timing.argtypes = [vp, i]
     L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
     _lib = L

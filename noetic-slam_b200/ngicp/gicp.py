@@ -92,6 +92,34 @@ class KdTreeFLANN:
         return keys, oh[:3].copy(), float(oh[3])
 
 
+class Keyframe:
+    """A keyframe held in HBM: the cloud and covariance list DLIO stores per keyframe (reference src/dlio/odom.cc:1592),
+    captured from the scan that was just registered. Additive API."""
+
+    def __init__(self, owner: "NanoGICP", ptr):
+        self._owner, self._L, self._kf = owner, owner._L, C.c_void_p(ptr)
+
+    def __del__(self):
+        if getattr(self, "_kf", None) and self._kf.value and self._owner._h.value:
+            self._L.ngicp_keyframe_release(self._owner._h, self._kf)
+            self._kf = C.c_void_p(None)
+
+    def size(self) -> int:
+        return int(self._L.ngicp_keyframe_size(self._kf))
+
+    def transform(self, T):
+        """pcl::transformPointCloud + cov <- Td cov Td^T (odom.cc:1757-1762), in place, on the device."""
+        t = np.ascontiguousarray(np.asarray(T, np.float32).T).reshape(16)
+        B.check(self._owner._h, self._L.ngicp_keyframe_transform(self._owner._h, self._kf, _ptr(t, C.c_float)))
+
+    def download(self):
+        n = self.size()
+        xyz = np.empty((n, 3), np.float32)
+        cov = np.empty((n, 4, 4), np.float64)
+        B.check(self._owner._h, self._L.ngicp_keyframe_download(self._owner._h, self._kf, _ptr(xyz, C.c_float), _ptr(cov, C.c_double)))
+        return xyz, cov.transpose(0, 2, 1).copy()
+
+
 class NanoGICP:
     """nano_gicp::NanoGICP<PointT,PointT> on one B200 (one CUDA stream per object)."""
 
@@ -313,6 +341,20 @@ class NanoGICP:
         B.check(self._h, self._L.ngicp_batch_linearize(self._h, S_, _ptr(t, C.c_double), _ptr(H, C.c_double), _ptr(b, C.c_double), _ptr(e, C.c_double),
                                                        _ptr(nc, C.c_int)))
         return e, H, b, nc
+
+    def captureKeyframe(self) -> Keyframe:
+        """Snapshot the current source cloud + covariances as a device-resident keyframe."""
+        kf = C.c_void_p(None)
+        B.check(self._h, self._L.ngicp_keyframe_capture(self._h, C.byref(kf)))
+        return Keyframe(self, kf.value)
+
+    def assembleSubmap(self, keyframes):
+        """buildSubmap (odom.cc:1719-1738) on the device: concatenated keyframes become the target cloud, its index and
+        its covariance list."""
+        arr = (C.c_void_p * len(keyframes))(*[k._kf.value for k in keyframes])
+        B.check(self._h, self._L.ngicp_submap_assemble(self._h, arr, len(keyframes)))
+        self.target_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.TARGET), None)
+        self._target = object()
 
     def enableTiming(self, on=True):
         B.check(self._h, self._L.ngicp_enable_timing(self._h, int(on)))

@@ -390,3 +390,41 @@ def test_batch_linearize_equals_per_scan_results():
     for i, (es, Hs, bs, ns) in enumerate(single):
         assert nc[i] == ns
         assert abs(e[i] - es) <= 1e-12 * abs(es) and np.abs(H[i] - Hs).max() <= 1e-12 * np.abs(Hs).max() and np.abs(bb[i] - bs).max() <= 1e-12 * np.abs(bs).max()
+
+
+def test_device_keyframe_store_matches_host_round_trip():
+    """keyframes captured, transformed and concatenated on the device give the submap (points,
+    covariances, pose) that DLIO's host round trip gives (odom.cc:1592,1719-1762,992-1005)."""
+    sc = synth.Scene(21); rng = np.random.default_rng(4)
+    poses = synth.trajectory(sc, 4, 21, step=1.0)
+    kscans = [synth.voxel_filter(synth.scan(sc, P, rng, w=128)) for P in poses[:3]]
+    src = synth.transform_points(poses[3], synth.voxel_filter(synth.scan(sc, poses[3], rng, w=128)))
+    src = synth.transform_points(np.linalg.inv(synth.se3((0, 0, 0.01), (0.1, -0.05, 0.0))), src)
+    g = S.configure(ngicp.NanoGICP(0))
+    kfs, host_pts, host_cov = [], [], []
+    for s_, P in zip(kscans, poses[:3]):
+        T = P.astype(np.float32)
+        g.setInputSource(s_); g.calculateSourceCovariances()
+        kf = g.captureKeyframe(); kf.transform(T); kfs.append(kf)
+        C_ = g.getSourceCovariances()                                   # host path: what DLIO does
+        Td = T.astype(np.float64)
+        host_cov.append(Td @ C_ @ Td.T)
+        host_pts.append((s_.astype(np.float32) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+    for kf, hp, hc in zip(kfs, host_pts, host_cov):
+        xyz, cov = kf.download()
+        assert np.abs(xyz - hp).max() < 2e-5 and np.abs(cov - hc).max() < 1e-6
+    g.assembleSubmap(kfs)
+    assert np.abs(g.getTargetCovariances() - np.concatenate(host_cov)).max() < 1e-6
+    g.setInputSource(src); g.calculateSourceCovariances()
+    T_dev = g.align().copy(); it_dev = g.nr_iterations_
+    h = S.configure(ngicp.NanoGICP(0))
+    h.setInputTarget(np.concatenate(host_pts)); h.setTargetCovariances(np.concatenate(host_cov))
+    h.setInputSource(src); h.calculateSourceCovariances()
+    T_host = h.align()
+    assert it_dev == h.nr_iterations_ and g.hasConverged() == h.hasConverged()
+    assert np.abs(T_dev - T_host).max() < 1e-5
+    o = S.configure(oracle.OracleGICP("port"))
+    o.setInputTarget(np.concatenate(host_pts)); o.setTargetCovariances(np.concatenate(host_cov))
+    o.setInputSource(src); o.calculateSourceCovariances()
+    To = o.align()
+    assert np.abs(T_dev[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(T_dev[:3, :3], To[:3, :3]) < POSE_R_TOL
