@@ -242,6 +242,8 @@ int ngicp_destroy(ngicp_handle* p) {
   }
   cudaStreamSynchronize(h->stream);
   if (h->corr) cudaFree(h->corr);
+  if (h->heavy) cudaFree(h->heavy);
+  if (h->heavy_count) cudaFree(h->heavy_count);
   if (h->partials) cudaFree(h->partials);
   if (h->batch_partials) cudaFree(h->batch_partials);
   if (h->counter) cudaFree(h->counter);

@@ -59,6 +59,9 @@ struct ngicp_handle {
   // registration scratch
   int* corr = nullptr;          // [n_src] target sorted position or -1 (order: source sorted position)
   size_t corr_cap = 0;
+  int2* heavy = nullptr;        // [corr_cap] (source sorted position, scan) of the queries the fast search kernel deferred
+  unsigned int* heavy_count = nullptr;   // [2] list lengths, alternating between searches (the heavy kernel clears the next one)
+  unsigned int heavy_parity = 0;
   size_t corr_n = 0;            // number of source points the cached correspondences belong to
   double lin_pose[12];          // pose of the last linearize (R row-major 9 + t 3), needed by compute_error
   bool lin_valid = false;

@@ -16,7 +16,7 @@
 
 #include "internal.h"
 #include "linearize.cuh"
-#include "wknn.cuh"
+#include "bnn.cuh"
 
 namespace ngicp {
 
@@ -167,68 +167,112 @@ __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* _
 }
 
 // K4a. Correspondence search (nano_gicp.cc:219-227): fp32 transform of every source point, exact 1-NN in the target
-// index, strict distance gate. grid = (blocks per scan, scans); source scan b = source segment b, its target segment is
-// target_seg[b] (or 0). Warps are persistent and take work items (32/LPQ consecutive points) round-robin, which
-// spreads the spatially clustered expensive items over the whole grid without giving up a fixed assignment.
-// corr[j] = target sorted position, or -2-pos for a neighbour that failed the gate (kept as a hint for the next
-// iteration), or -1.
-template <int LPQ, bool USE_PREV>
-__global__ void __launch_bounds__(kLinThreads) correspond_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
-                                                                  const int* __restrict__ target_seg, double thr2, float max_sqd, int cmax,
-                                                                  int* __restrict__ corr) {
+// index, strict distance gate. Two kernels (bnn.cuh): the fast one resolves every query whose bounded ball is small
+// and lists the rest; the heavy one gives each listed query a whole warp. grid.y = scans; source scan b = source
+// segment b, its target segment is target_seg[b] (or 0).
+// corr[j] = target sorted position, or -2-pos for a neighbour that failed the gate / a bound that is not yet the
+// answer (both are hints for the next search of this point), or -1.
+__device__ __forceinline__ void transform_query(const PoseArg& P, const float4& pa, float qf[3]) {
+  // ((r0*x + r1*y) + r2*z) + t*w with w = 1, fp32 (nano_gicp.cc:222)
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
+}
+__device__ __forceinline__ int corr_code(int pos, float d, double thr2) {
+  const bool valid = pos >= 0 && (double)d < thr2;                     // strict, float promoted to double (nano_gicp.cc:227)
+  return valid ? pos : (pos >= 0 ? -2 - pos : -1);
+}
+__device__ __forceinline__ int corr_hint(int c) { return c >= 0 ? c : (c <= -2 ? -2 - c : -1); }
+
+template <bool USE_PREV>
+__global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
+                                                                       const int* __restrict__ target_seg, double thr2, float max_sqd,
+                                                                       int* __restrict__ corr, int2* __restrict__ heavy, unsigned int* __restrict__ heavy_count) {
   const PoseArg P = load_pose(pose0, poses);
   const int b = blockIdx.y;
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
   const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
   const int tseg = target_seg ? __ldg(target_seg + b) : 0;
-  __shared__ WarpScratch scratch[kLinThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kPer = 32 / LPQ;                      // points per work item
+  constexpr int LPQ = 4, kPer = 32 / LPQ;
   const int gwarp = blockIdx.x * (kLinThreads / 32) + warp, nwarps = gridDim.x * (kLinThreads / 32);
-  uint32_t phase = wknn_init(scratch[warp]);
-#ifdef NGICP_STATS
-  const long long t_warp0 = clock64();
-#endif
-  for (int j0 = begin + gwarp * kPer; j0 < end; j0 += nwarps * kPer) {   // warp-uniform: the whole warp searches together
-#ifdef NGICP_STATS
-    const long long t_item0 = clock64();
-#endif
+  for (int j0 = begin + gwarp * kPer; j0 < end; j0 += nwarps * kPer) {
     const int j = j0 + lane / LPQ;
     const bool active = j < end;
-    const float4 pa = active ? __ldg(src.pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    // fp32 transform of the query, ((r0*x + r1*y) + r2*z) + t*w with w = 1 (nano_gicp.cc:222)
-    float qf[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-      qf[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Rf[3 * r], pa.x), __fmul_rn(P.Rf[3 * r + 1], pa.y)), __fmul_rn(P.Rf[3 * r + 2], pa.z)), P.tf[r]);
-    // Re-association after a small pose update: the previous nearest neighbour, re-measured at the new pose, bounds
-    // the search to a small ball (wknn.cuh: ball_search). Same exact result, a fraction of the work.
-    bool resolved = false;
-    float nd = __int_as_float(0x7f800000);
-    int ni = -1;
-    if (USE_PREV && active) {
-      const int c = corr[j];
-      const int prev = c >= 0 ? c : (c <= -2 ? -2 - c : -1);
-      if (prev >= 0) {
-        const float4 pb0 = __ldg(tgt.pts + prev);
-        resolved = ball_search<LPQ>(tgt, qf[0], qf[1], qf[2], tseg, sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z), __float_as_int(pb0.w), nd, ni);
+    bool is_heavy = false;
+    if (active) {
+      const float4 pa = __ldg(src.pts + j);
+      float qf[3];
+      transform_query(P, pa, qf);
+      NNBest best;
+      bool have = false;
+      if (USE_PREV) {
+        const int prev = corr_hint(corr[j]);
+        if (prev >= 0) {
+          const float4 pb0 = __ldg(tgt.pts + prev);
+          have = true;
+          best.d = sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z);
+          best.i = __float_as_int(pb0.w);
+          best.pos = prev;
+        }
       }
+      const bool resolved = bnn_group(tgt, qf[0], qf[1], qf[2], tseg, have, max_sqd, best);
+      is_heavy = !resolved && (lane & (LPQ - 1)) == 0;
+      if ((lane & (LPQ - 1)) == 0) corr[j] = resolved ? corr_code(best.pos, best.d, thr2) : (best.pos >= 0 ? -2 - best.pos : -1);
     }
-    TopK<1> best;
-    warp_knn<LPQ>(tgt, active && !resolved, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp], phase);
-    if (!resolved) { nd = best.d[0]; ni = best.p[0]; }
-    if (active && (lane & (LPQ - 1)) == 0) {
-      const int pos = ni >= 0 ? __ldg(tgt.inv + ni) : -1;                 // original index -> sorted position
-      const bool valid = pos >= 0 && (double)nd < thr2;                   // strict, float promoted to double (nano_gicp.cc:227)
-      corr[j] = valid ? pos : (pos >= 0 ? -2 - pos : -1);
+    // one atomic per warp reserves list slots for its heavy queries
+    const unsigned hm = __ballot_sync(0xffffffffu, is_heavy);
+    if (hm) {
+      unsigned int slot = 0;
+      if (lane == __ffs(hm) - 1) slot = atomicAdd(heavy_count, (unsigned int)__popc(hm));
+      slot = __shfl_sync(0xffffffffu, slot, __ffs(hm) - 1);
+      if (is_heavy) heavy[slot + __popc(hm & ((1u << lane) - 1u))] = make_int2(j, b);
     }
-#ifdef NGICP_STATS
-    if (lane == 0) { const long long dt = clock64() - t_item0; g_item_cycles[((j0 - begin) / kPer) & 0xffff] = (unsigned int)dt; int bkt = 0; while ((1ll << (bkt + 10)) < dt && bkt < 15) bkt++; atomicAdd(&g_lin_hist[bkt], 1ull); }
-#endif
   }
-#ifdef NGICP_STATS
-  if (lane == 0) { const long long dt = clock64() - t_warp0; int bkt = 0; while ((1ll << (bkt + 10)) < dt && bkt < 15) bkt++; atomicAdd(&g_lin_hist[16 + bkt], 1ull); }
-#endif
+}
+
+__global__ void __launch_bounds__(kLinThreads) correspond_heavy_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
+                                                                        const int* __restrict__ target_seg, double thr2, float max_sqd, int cmax,
+                                                                        int* __restrict__ corr, const int2* __restrict__ heavy,
+                                                                        const unsigned int* __restrict__ heavy_count, unsigned int* __restrict__ next_count) {
+  __shared__ WarpScratch scratch[kLinThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int count = __ldg(heavy_count);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;      // the list of the next search starts empty
+  const int gwarp = blockIdx.x * (kLinThreads / 32) + warp, nwarps = gridDim.x * (kLinThreads / 32);
+  if ((unsigned int)gwarp >= count) return;
+  uint32_t phase = wknn_init(scratch[warp]);
+  for (unsigned int e = gwarp; e < count; e += nwarps) {
+    const int2 jb = __ldg(heavy + e);
+    const int j = jb.x;
+    const PoseArg* Pp = poses ? poses + jb.y : &pose0;
+    PoseArg P;   // only the fp32 part is used
+#pragma unroll
+    for (int i = 0; i < 9; i++) P.Rf[i] = Pp->Rf[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) P.tf[i] = Pp->tf[i];
+    const int tseg = target_seg ? __ldg(target_seg + jb.y) : 0;
+    const float4 pa = __ldg(src.pts + j);
+    float qf[3];
+    transform_query(P, pa, qf);
+    float bd = __int_as_float(0x7f800000);
+    int bp = -1;
+    const int prev = corr_hint(corr[j]);
+    if (prev >= 0) {
+      const float4 pb0 = __ldg(tgt.pts + prev);
+      bd = sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z);
+      bp = __float_as_int(pb0.w);
+    }
+    if (!(bd <= max_sqd)) { bd = max_sqd; bp = -1; }
+    if (!bnn_warp(tgt, qf[0], qf[1], qf[2], tseg, bd, bp, scratch[warp], phase)) {
+      // ball larger than the bounded search handles: general search, lanes 0..3 carry the query
+      TopK<1> best;
+      warp_knn<4>(tgt, lane < 4, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp], phase);
+      bd = __shfl_sync(0xffffffffu, best.d[0], 0);
+      bp = __shfl_sync(0xffffffffu, best.p[0], 0);
+    }
+    if (lane == 0) corr[j] = corr_code(bp >= 0 ? __ldg(tgt.inv + bp) : -1, bd, thr2);
+  }
 }
 
 // K4b. Fused linearisation (nano_gicp.cc:237-241,259-299): per matched source point the Mahalanobis matrix
@@ -443,8 +487,14 @@ static int check_ready(Handle* h) {
 static int ensure_corr(Handle* h, size_t n) {
   if (h->corr_cap >= n) return NGICP_OK;
   if (h->corr) NGICP_CUDA(h, cudaFree(h->corr));
-  h->corr = nullptr; h->corr_cap = 0;
+  if (h->heavy) NGICP_CUDA(h, cudaFree(h->heavy));
+  h->corr = nullptr; h->heavy = nullptr; h->corr_cap = 0;
   NGICP_CUDA(h, cudaMalloc(&h->corr, sizeof(int) * n));
+  NGICP_CUDA(h, cudaMalloc(&h->heavy, sizeof(int2) * n));
+  if (!h->heavy_count) {
+    NGICP_CUDA(h, cudaMalloc(&h->heavy_count, sizeof(unsigned int) * 2));
+    NGICP_CUDA(h, cudaMemsetAsync(h->heavy_count, 0, sizeof(unsigned int) * 2, h->stream));
+  }
   h->corr_cap = n;
   return NGICP_OK;
 }
@@ -464,20 +514,25 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   const Index* ti = h->index[1];
   const double thr = h->params.max_corr_dist;
   const double thr2 = thr * thr;
-  const int lpq = h->k4_lpq > 0 ? h->k4_lpq : 4;
   const int per_scan = si->n / n_scans + 1;
-  const dim3 sgrid(search_blocks_for(per_scan, lpq >= 4 ? 4 : 1), n_scans);
+  const dim3 sgrid(search_blocks_for(per_scan, 4), n_scans);
+  const int hgrid = 148 * 6;   // heavy queries: one warp each, persistent over the list
   // batched: few fat blocks per scan (many points per thread amortise the 29-term block reduction); single scan: wide
   const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * 8) / n_scans)), n_scans);
   // the correspondences of the previous linearize (same clouds) seed this one
   const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
+  unsigned int* cnt = h->heavy_count + (h->heavy_parity & 1u);
+  unsigned int* cnt_next = h->heavy_count + ((h->heavy_parity + 1u) & 1u);
+  h->heavy_parity++;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-#define LAUNCH_CORR(LPQ, PREV)                                                                                                  \
-  correspond_kernel<LPQ, PREV><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, \
-                                                                     max_sqd_for(thr), h->k4_cmax, h->corr)
-  if (lpq >= 4) { if (use_prev) LAUNCH_CORR(4, true); else LAUNCH_CORR(4, false); }
-  else { if (use_prev) LAUNCH_CORR(1, true); else LAUNCH_CORR(1, false); }
-#undef LAUNCH_CORR
+  if (use_prev)
+    correspond_fast_kernel<true><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
+                                                                       h->heavy, cnt);
+  else
+    correspond_fast_kernel<false><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
+                                                                        h->heavy, cnt);
+  correspond_heavy_kernel<<<hgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->k4_cmax,
+                                                                h->corr, h->heavy, cnt, cnt_next);
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
   if (want_Hb)
     linearize_kernel<true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
@@ -486,7 +541,7 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
     linearize_kernel<false><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
                                                                  h->counter, h->slot_dev, seq);
   h->corr_n = (size_t)si->n;
-  count_launch(h, 2);
+  count_launch(h, 3);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);
   if (int rc = wait_slot(h, n_scans, seq)) return rc;

@@ -33,9 +33,9 @@ static __device__ unsigned long long g_wknn_stats[8];
 
 struct __align__(16) WarpScratch {
   float4 pts[2][kWarpChunk];    // staged candidates, double buffered (written by the TMA bulk copies)
-  uint32_t rstart[64];          // non-empty voxel buckets of the block, compacted, in scan order
-  uint32_t rpre[65];            // exclusive prefix of their sizes; rpre[R] = M
-  uint32_t pad;
+  uint32_t rstart[128];         // non-empty voxel buckets of the block (<= 64) or ball (<= 125), compacted, in scan order
+  uint32_t rpre[129];           // exclusive prefix of their sizes; rpre[R] = M
+  uint32_t pad[3];
   unsigned long long mbar[2];   // one mbarrier per buffer: the bulk copies complete on it
   float4 qm[8];                 // member queries of the current pass (k = 1 path)
 };
@@ -97,67 +97,6 @@ __device__ __forceinline__ void wknn_wait(WarpScratch& ws, int buf, uint32_t& ph
       __syncwarp();                                                                                        \
     }                                                                                                      \
   }
-
-// Exact nearest neighbour when an upper bound is already known (the correspondence of the previous LM iteration,
-// re-measured at the new pose): every point that can beat or tie the bound lies in the closed ball of radius
-// sqrt(d_ub) around the query, which at the level whose cell side is >= the ball's diameter touches at most
-// 2x2x2 cells. The LPQ lanes of the query split those cells and merge with shuffles inside their group.
-// Returns false (nothing searched) when the ball is too large for this shortcut to pay off.
-constexpr int kBallMaxLevelsAboveBase = 2;
-template <int LPQ>
-__device__ __forceinline__ bool ball_search(const GridView& g, float qx, float qy, float qz, int seg, float d_ub, int i_ub,
-                                            float& bd, int& bp) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & (LPQ - 1);
-  const GridMeta* __restrict__ m = g.meta;
-  const float h0 = __ldg(&m->h0), inv_h0 = __ldg(&m->inv_h0), margin = __ldg(&m->margin);
-  const int base = __ldg(&m->base_level);
-  const float4 o = __ldg(g.seg_origin + seg);
-  const float ux = __fsub_rn(qx, o.x), uy = __fsub_rn(qy, o.y), uz = __fsub_rn(qz, o.z);
-  const float r = __fsqrt_ru(d_ub) * 1.000001f + margin;   // covers the fp32 rounding of the metric and of the keys
-  int L = base;
-  float hL = h0 * (float)(1 << base);
-  while (hL < 2.0f * r && L < kTopLevel) { hL *= 2.0f; L++; }
-  if (L > base + kBallMaxLevelsAboveBase) return false;
-  const float inv_hL = inv_h0 / (float)(1 << L);            // powers of two: exact
-  const int maxc = kMaxCoord >> L;
-  const int lox = max((int)floorf((ux - r) * inv_hL), 0), hix = min((int)floorf((ux + r) * inv_hL), maxc);
-  const int loy = max((int)floorf((uy - r) * inv_hL), 0), hiy = min((int)floorf((uy + r) * inv_hL), maxc);
-  const int loz = max((int)floorf((uz - r) * inv_hL), 0), hiz = min((int)floorf((uz + r) * inv_hL), maxc);
-  const int nx = hix - lox + 1, ny = hiy - loy + 1, nz = hiz - loz + 1;
-  if (nx > 2 || ny > 2 || nz > 2) return false;             // cannot happen for hL >= 2r; stay exact if it ever does
-  bd = d_ub;
-  bp = i_ub;
-  const int total = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
-  for (int c = sub; c < total; c += LPQ) {
-    const int ix = lox + c % nx, iy = loy + (c / nx) % ny, iz = loz + c / (nx * ny);
-    const unsigned long long ck = pack_cell((unsigned)seg, L, (unsigned)ix, (unsigned)iy, (unsigned)iz);
-    uint32_t s, e;
-    if (!cell_lookup(g.table, g.table_mask, ck, s, e)) continue;
-    // four independent loads in flight per step: a serial load->compare chain would pay one memory latency per point
-    for (uint32_t j = s; j < e; j += 4) {
-      float4 p[4];
-#pragma unroll
-      for (int t = 0; t < 4; t++) p[t] = __ldg(g.pts + min(j + t, e - 1));
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const float d = sqdist_ref(qx, qy, qz, p[t].x, p[t].y, p[t].z);
-        const int pi = __float_as_int(p[t].w);
-        if (TopK<1>::before(d, pi, bd, bp)) { bd = d; bp = pi; }   // re-offering a duplicate of the last point is harmless
-      }
-    }
-  }
-  if (LPQ > 1) {
-    const unsigned gmask = ((LPQ == 32) ? 0xffffffffu : ((1u << LPQ) - 1u)) << (lane & ~(LPQ - 1));
-#pragma unroll
-    for (int off = LPQ / 2; off > 0; off >>= 1) {
-      const float od = __shfl_xor_sync(gmask, bd, off);
-      const int op = __shfl_xor_sync(gmask, bp, off);
-      if (TopK<1>::before(od, op, bd, bp)) { bd = od; bp = op; }
-    }
-  }
-  return true;
-}
 
 // Once per warp and kernel, before the first warp_knn: arm the warp's mbarrier. (Initialising an mbarrier twice is
 // undefined, so persistent kernels that search many times keep one barrier and carry its phase parity along.)
