@@ -8,8 +8,8 @@
 // the query's own base-level cell (or its parent), clipped to max_sqd.
 //
 // Two stages, two kernels (linearize.cu):
-//   bnn_group  4 lanes per query, registers only. Resolves the LIGHT queries: ball within <= 16 base-level cells
-//              (one batch of four hash probes per lane, then the points of those cells as one flat list, four loads
+//   bnn_group  4 lanes per query, registers only. Resolves the LIGHT queries: ball within <= 32 base-level cells
+//              (batches of four hash probes per lane, then the points of those cells as one flat list, four loads
 //              in flight). A query never waits for the other queries of its warp beyond that fixed, short chain.
 //              Everything else is HEAVY: its best known bound is left behind as a hint and its index is appended to
 //              a list.
@@ -24,7 +24,7 @@
 namespace ngicp {
 
 constexpr int kBnnSeedPerLane = 8;            // seed points examined per lane (own cell, 4 lanes)
-constexpr int kBnnLightCells = 16;            // a light query touches at most this many base-level cells
+constexpr int kBnnLightCells = 32;            // a light query touches at most this many base-level cells (two batches of 4 probes per lane)
 constexpr int kBnnSpan = 5;                   // heavy: cells per axis the ball may span at the chosen level
 constexpr int kBnnMaxLevelsAboveBase = 2;
 
@@ -140,22 +140,24 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
   if (!(best.d <= max_sqd)) { best.d = max_sqd; best.i = -1; best.pos = -1; }   // also "no bound at all" (+inf)
   const float r = __fsqrt_ru(best.d) * 1.000001f + margin;   // covers the fp32 rounding of the metric and of the keys
   const float hL = h0 * (float)(1 << base);
-  if (!(r <= 2.0f * hL)) return false;                       // also r = +inf / NaN
+  if (sub == 0) { BNN_STAT(0, 1); if (best.i < 0) BNN_STAT(5, 1); if (have_hint) BNN_STAT(4, 1); }
+  if (!(r <= 2.0f * hL)) { if (sub == 0) BNN_STAT(1, 1); return false; }                       // also r = +inf / NaN
   const float inv_hL = inv_h0 / (float)(1 << base);          // powers of two: exact
   const BallCells bc = bnn_cells(ux, uy, uz, r, inv_hL, kMaxCoord >> base);
-  if (bc.total > kBnnLightCells) return false;
-  // ---- one batch of up to four probes per lane
+  if (bc.total > kBnnLightCells) { if (sub == 0) BNN_STAT(2, 1); return false; }
+  // ---- batches of four probes per lane
   const unsigned int rx = (65536u + (unsigned)max(bc.nx, 1) - 1u) / (unsigned)max(bc.nx, 1);   // c / nx == (c * rx) >> 16 for c < 125
   const unsigned int ry = (65536u + (unsigned)max(bc.ny, 1) - 1u) / (unsigned)max(bc.ny, 1);
   const float slack = 2.0f * margin;
-  constexpr int NB = kBnnLightCells / LPQ;
+  constexpr int NB = 4;
+  for (int cb = 0; cb < bc.total; cb += NB * LPQ) {          // uniform in the group
   unsigned long long ck[NB];
   uint32_t hh[NB];
   uint4 raw[NB];
   bool want[NB];
 #pragma unroll
   for (int t = 0; t < NB; t++) {
-    const int c = sub + LPQ * t;
+    const int c = cb + sub + LPQ * t;
     const int cyz = (int)(((unsigned)c * rx) >> 16);
     const int ox = c - cyz * bc.nx;
     const int oz = (int)(((unsigned)cyz * ry) >> 16);
@@ -194,14 +196,16 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
     for (int u = 0; u < 4; u++)   // re-offering a duplicate of the last point is harmless
       nn_offer(best, sqdist_ref(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), (int)pos[u]);
   }
+  }
   nn_reduce<LPQ>(best, gmask);
   return true;
 }
 
 // ---------------------------------------------------------------------------------------------- stage 2
-// One warp, one query (all lanes hold identical inputs). bd/bp: in = bound already clipped to max_sqd (bp = -1 if it
-// is only the clip), out = exact nearest neighbour within the bound. Returns false when the ball is too large.
-__device__ __forceinline__ bool bnn_warp(const GridView& g, float qx, float qy, float qz, int seg, float& bd, int& bp, WarpScratch& ws, uint32_t& phase) {
+// One warp, one query (all lanes hold identical inputs). best: in = bound already clipped to max_sqd (i = pos = -1 if
+// it is only the clip), out = exact nearest neighbour within the bound. Returns false when the ball is too large.
+__device__ __forceinline__ bool bnn_warp(const GridView& g, float qx, float qy, float qz, int seg, NNBest& best, WarpScratch& ws, uint32_t& phase) {
+  const float bd = best.d;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const GridMeta* __restrict__ m = g.meta;
@@ -214,7 +218,8 @@ __device__ __forceinline__ bool bnn_warp(const GridView& g, float qx, float qy, 
   int L = base;
   float hL = h0 * (float)(1 << base);
   while (hL * (0.5f * (kBnnSpan - 1)) < r && L < base + kBnnMaxLevelsAboveBase && L < kTopLevel) { hL *= 2.0f; L++; }
-  if (!(hL * (0.5f * (kBnnSpan - 1)) >= r)) return false;
+  if (!(hL * (0.5f * (kBnnSpan - 1)) >= r)) { if (lane == 0) BNN_STAT(10, 1); return false; }
+  if (lane == 0) { BNN_STAT(6, 1); BNN_STAT(7 + (L - base), 1); }
   const float inv_hL = inv_h0 / (float)(1 << L);
   const BallCells bc = bnn_cells(ux, uy, uz, r, inv_hL, kMaxCoord >> L);
   if (bc.nx > kBnnSpan || bc.ny > kBnnSpan || bc.nz > kBnnSpan) return false;   // cannot happen; stay exact if it ever does
@@ -265,26 +270,31 @@ __device__ __forceinline__ bool bnn_warp(const GridView& g, float qx, float qy, 
     R += __popc(nz);
   }
   if (lane == 0) ws.rpre[R] = M;
+  if (lane == 0) { BNN_STAT(11, M); BNN_STAT(12, R); BNN_STAT(13, bc.total); }
   __syncwarp();
-  float md = __int_as_float(0x7f800000);
-  int mp = -1;
+  NNBest mine;   // pos = number of the candidate in the concatenated bucket list
+  mine.d = __int_as_float(0x7f800000); mine.i = -1; mine.pos = -1;
   WKNN_FOR_CHUNKS({
 #pragma unroll
     for (int t = 0; t < kWarpChunk / 32; t++) {
       const int e = lane + 32 * t;
       const float4 c = P[min(e, nch - 1)];
       const float d = sqdist_ref(qx, qy, qz, c.x, c.y, c.z);
-      const int pi = __float_as_int(c.w);
-      if (e < nch && TopK<1>::before(d, pi, md, mp)) { md = d; mp = pi; }
+      if (e < nch) nn_offer(mine, d, __float_as_int(c.w), (int)c0 + e);
     }
   })
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float od = __shfl_xor_sync(FULL, md, off);
-    const int op = __shfl_xor_sync(FULL, mp, off);
-    if (TopK<1>::before(od, op, md, mp)) { md = od; mp = op; }
+  nn_reduce<32>(mine, FULL);
+  if (mine.i >= 0 && TopK<1>::before(mine.d, mine.i, best.d, best.i)) {
+    // candidate number -> sorted position: the bucket that holds it (shared-memory binary search, uniform)
+    int lo = 0, hi = R;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ws.rpre[mid] <= (uint32_t)mine.pos) lo = mid; else hi = mid;
+    }
+    best.d = mine.d; best.i = mine.i;
+    best.pos = (int)(ws.rstart[lo] + ((uint32_t)mine.pos - ws.rpre[lo]));
   }
-  if (mp >= 0 && TopK<1>::before(md, mp, bd, bp)) { bd = md; bp = mp; }
+  __syncwarp();
   return true;
 }
 

@@ -59,7 +59,7 @@ struct ngicp_handle {
   // registration scratch
   int* corr = nullptr;          // [n_src] target sorted position or -1 (order: source sorted position)
   size_t corr_cap = 0;
-  int2* heavy = nullptr;        // [corr_cap] (source sorted position, scan) of the queries the fast search kernel deferred
+  void* heavy = nullptr;        // [corr_cap] HeavyQuery (linearize.cu): the queries the fast search kernel deferred
   unsigned int* heavy_count = nullptr;   // [2] list lengths, alternating between searches (the heavy kernel clears the next one)
   unsigned int heavy_parity = 0;
   size_t corr_n = 0;            // number of source points the cached correspondences belong to

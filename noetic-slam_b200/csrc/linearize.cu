@@ -184,10 +184,17 @@ __device__ __forceinline__ int corr_code(int pos, float d, double thr2) {
 }
 __device__ __forceinline__ int corr_hint(int c) { return c >= 0 ? c : (c <= -2 ? -2 - c : -1); }
 
+// a query the fast kernel deferred: transformed point, bound (squared distance, original index, sorted position; the
+// clip to max_sqd has i = pos = -1), its place in the correspondence array and its target segment
+struct __align__(16) HeavyQuery {
+  float4 q;   // x, y, z, bound d
+  int4 m;     // bound i, bound pos, j, target segment
+};
+
 template <bool USE_PREV>
 __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
                                                                        const int* __restrict__ target_seg, double thr2, float max_sqd,
-                                                                       int* __restrict__ corr, int2* __restrict__ heavy, unsigned int* __restrict__ heavy_count) {
+                                                                       int* __restrict__ corr, HeavyQuery* __restrict__ heavy, unsigned int* __restrict__ heavy_count) {
   const PoseArg P = load_pose(pose0, poses);
   const int b = blockIdx.y;
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
@@ -200,11 +207,12 @@ __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView s
     const int j = j0 + lane / LPQ;
     const bool active = j < end;
     bool is_heavy = false;
+    float qf[3] = {0.f, 0.f, 0.f};
+    NNBest best;
+    best.d = 0.f; best.i = -1; best.pos = -1;
     if (active) {
       const float4 pa = __ldg(src.pts + j);
-      float qf[3];
       transform_query(P, pa, qf);
-      NNBest best;
       bool have = false;
       if (USE_PREV) {
         const int prev = corr_hint(corr[j]);
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView s
       }
       const bool resolved = bnn_group(tgt, qf[0], qf[1], qf[2], tseg, have, max_sqd, best);
       is_heavy = !resolved && (lane & (LPQ - 1)) == 0;
-      if ((lane & (LPQ - 1)) == 0) corr[j] = resolved ? corr_code(best.pos, best.d, thr2) : (best.pos >= 0 ? -2 - best.pos : -1);
+      if (resolved && (lane & (LPQ - 1)) == 0) corr[j] = corr_code(best.pos, best.d, thr2);
     }
     // one atomic per warp reserves list slots for its heavy queries
     const unsigned hm = __ballot_sync(0xffffffffu, is_heavy);
@@ -226,15 +234,18 @@ __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView s
       unsigned int slot = 0;
       if (lane == __ffs(hm) - 1) slot = atomicAdd(heavy_count, (unsigned int)__popc(hm));
       slot = __shfl_sync(0xffffffffu, slot, __ffs(hm) - 1);
-      if (is_heavy) heavy[slot + __popc(hm & ((1u << lane) - 1u))] = make_int2(j, b);
+      if (is_heavy) {
+        HeavyQuery* q = heavy + slot + __popc(hm & ((1u << lane) - 1u));
+        q->q = make_float4(qf[0], qf[1], qf[2], best.d);
+        q->m = make_int4(best.i, best.pos, j, tseg);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(kLinThreads) correspond_heavy_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
-                                                                        const int* __restrict__ target_seg, double thr2, float max_sqd, int cmax,
-                                                                        int* __restrict__ corr, const int2* __restrict__ heavy,
-                                                                        const unsigned int* __restrict__ heavy_count, unsigned int* __restrict__ next_count) {
+__global__ void __launch_bounds__(kLinThreads, 5) correspond_heavy_kernel(GridView tgt, double thr2, float max_sqd, int cmax, int* __restrict__ corr,
+                                                                           const HeavyQuery* __restrict__ heavy, const unsigned int* __restrict__ heavy_count,
+                                                                           unsigned int* __restrict__ next_count) {
   __shared__ WarpScratch scratch[kLinThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned int count = __ldg(heavy_count);
@@ -243,35 +254,20 @@ __global__ void __launch_bounds__(kLinThreads) correspond_heavy_kernel(GridView 
   if ((unsigned int)gwarp >= count) return;
   uint32_t phase = wknn_init(scratch[warp]);
   for (unsigned int e = gwarp; e < count; e += nwarps) {
-    const int2 jb = __ldg(heavy + e);
-    const int j = jb.x;
-    const PoseArg* Pp = poses ? poses + jb.y : &pose0;
-    PoseArg P;   // only the fp32 part is used
-#pragma unroll
-    for (int i = 0; i < 9; i++) P.Rf[i] = Pp->Rf[i];
-#pragma unroll
-    for (int i = 0; i < 3; i++) P.tf[i] = Pp->tf[i];
-    const int tseg = target_seg ? __ldg(target_seg + jb.y) : 0;
-    const float4 pa = __ldg(src.pts + j);
-    float qf[3];
-    transform_query(P, pa, qf);
-    float bd = __int_as_float(0x7f800000);
-    int bp = -1;
-    const int prev = corr_hint(corr[j]);
-    if (prev >= 0) {
-      const float4 pb0 = __ldg(tgt.pts + prev);
-      bd = sqdist_ref(qf[0], qf[1], qf[2], pb0.x, pb0.y, pb0.z);
-      bp = __float_as_int(pb0.w);
-    }
-    if (!(bd <= max_sqd)) { bd = max_sqd; bp = -1; }
-    if (!bnn_warp(tgt, qf[0], qf[1], qf[2], tseg, bd, bp, scratch[warp], phase)) {
+    const float4 q = __ldg(&heavy[e].q);
+    const int4 m = __ldg(&heavy[e].m);
+    NNBest best;
+    best.d = q.w; best.i = m.x; best.pos = m.y;
+    const int j = m.z, tseg = m.w;
+    if (!bnn_warp(tgt, q.x, q.y, q.z, tseg, best, scratch[warp], phase)) {
       // ball larger than the bounded search handles: general search, lanes 0..3 carry the query
-      TopK<1> best;
-      warp_knn<4>(tgt, lane < 4, qf[0], qf[1], qf[2], tseg, 1, cmax, max_sqd, best, scratch[warp], phase);
-      bd = __shfl_sync(0xffffffffu, best.d[0], 0);
-      bp = __shfl_sync(0xffffffffu, best.p[0], 0);
+      TopK<1> top;
+      warp_knn<4>(tgt, lane < 4, q.x, q.y, q.z, tseg, 1, cmax, max_sqd, top, scratch[warp], phase);
+      best.d = __shfl_sync(0xffffffffu, top.d[0], 0);
+      best.i = __shfl_sync(0xffffffffu, top.p[0], 0);
+      best.pos = best.i >= 0 ? __ldg(tgt.inv + best.i) : -1;
     }
-    if (lane == 0) corr[j] = corr_code(bp >= 0 ? __ldg(tgt.inv + bp) : -1, bd, thr2);
+    if (lane == 0) corr[j] = corr_code(best.pos, best.d, thr2);
   }
 }
 
@@ -490,7 +486,7 @@ static int ensure_corr(Handle* h, size_t n) {
   if (h->heavy) NGICP_CUDA(h, cudaFree(h->heavy));
   h->corr = nullptr; h->heavy = nullptr; h->corr_cap = 0;
   NGICP_CUDA(h, cudaMalloc(&h->corr, sizeof(int) * n));
-  NGICP_CUDA(h, cudaMalloc(&h->heavy, sizeof(int2) * n));
+  NGICP_CUDA(h, cudaMalloc(&h->heavy, sizeof(HeavyQuery) * n));
   if (!h->heavy_count) {
     NGICP_CUDA(h, cudaMalloc(&h->heavy_count, sizeof(unsigned int) * 2));
     NGICP_CUDA(h, cudaMemsetAsync(h->heavy_count, 0, sizeof(unsigned int) * 2, h->stream));
@@ -516,7 +512,7 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   const double thr2 = thr * thr;
   const int per_scan = si->n / n_scans + 1;
   const dim3 sgrid(search_blocks_for(per_scan, 4), n_scans);
-  const int hgrid = 148 * 6;   // heavy queries: one warp each, persistent over the list
+  const int hgrid = 148 * 5;   // heavy queries: one warp each, persistent over the list
   // batched: few fat blocks per scan (many points per thread amortise the 29-term block reduction); single scan: wide
   const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * 8) / n_scans)), n_scans);
   // the correspondences of the previous linearize (same clouds) seed this one
@@ -527,12 +523,12 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
   if (use_prev)
     correspond_fast_kernel<true><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
-                                                                       h->heavy, cnt);
+                                                                       static_cast<HeavyQuery*>(h->heavy), cnt);
   else
     correspond_fast_kernel<false><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
-                                                                        h->heavy, cnt);
-  correspond_heavy_kernel<<<hgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->k4_cmax,
-                                                                h->corr, h->heavy, cnt, cnt_next);
+                                                                        static_cast<HeavyQuery*>(h->heavy), cnt);
+  correspond_heavy_kernel<<<hgrid, kLinThreads, 0, h->stream>>>(ti->view(), thr2, max_sqd_for(thr), h->k4_cmax, h->corr,
+                                                                static_cast<const HeavyQuery*>(h->heavy), cnt, cnt_next);
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
   if (want_Hb)
     linearize_kernel<true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
@@ -696,6 +692,12 @@ extern "C" int ngicp_debug_stats_lin(unsigned long long out[8], int reset) {
 #endif
 
 #ifdef NGICP_STATS
+extern "C" int ngicp_debug_bnn(unsigned long long out[16], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_bnn_stats, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ngicp::g_bnn_stats, z, sizeof z); }
+  return 0;
+}
 extern "C" int ngicp_debug_lin_hist(unsigned long long out[32], int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, ngicp::g_lin_hist, sizeof(unsigned long long) * 32);

@@ -27,8 +27,11 @@ constexpr int kWarpChunk = 256;  // candidates staged per pass and warp
 // development counters: [0] passes, [1] staged candidates, [2] member lanes, [3] warp_knn calls, [4] refused members
 static __device__ unsigned long long g_wknn_stats[8];
 #define WKNN_STAT(i, v) do { const unsigned long long _sv = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_wknn_stats[i], _sv); } while (0)
+static __device__ unsigned long long g_bnn_stats[16];
+#define BNN_STAT(i, v) atomicAdd(&g_bnn_stats[i], (unsigned long long)(v))
 #else
 #define WKNN_STAT(i, v) do { } while (0)
+#define BNN_STAT(i, v) do { } while (0)
 #endif
 
 struct __align__(16) WarpScratch {
