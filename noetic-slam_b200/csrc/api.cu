@@ -130,14 +130,12 @@ int compute_covariances_impl(Handle* h, int which, float* density) {
     StageTimer t(h, &h->t.covariance_ms);
     rc = covariances_from_knn(h, idx, d_nbr, k, h->params.regularization, c.cov6);
   }
-  if (!rc) rc = reduce_sum(h, d_dens, (int)n, idx->seg_start, idx->n_seg, d_sum);
-  if (!rc && density) {
-    // density = sum / N (nano_gicp.cc:389); one 8-byte read-back. Callers that do not need the
-    // value pass NULL and stay asynchronous.
+  if (!rc && density && idx->n_seg == 1) {
+    // density = sum / N (nano_gicp.cc:389): the kernel delivers the sum to host-mapped memory. Callers that do not
+    // need the value pass NULL and stay asynchronous.
     double sum = 0.0;
-    if (idx->n_seg == 1) {
-      NGICP_CUDA(h, cudaMemcpyAsync(&sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
-      NGICP_CUDA(h, cudaStreamSynchronize(s));
+    rc = reduce_sum(h, d_dens, (int)n, idx->seg_start, 1, &sum);
+    if (!rc) {
       c.density = (float)(sum / (double)n);
       *density = c.density;
     }
@@ -692,7 +690,6 @@ int ngicp_batch_covariances(ngicp_handle* p, const void* points, size_t n, size_
     StageTimer t(h, &h->t.covariance_ms);
     rc = covariances_from_knn(h, idx, d_nbr, k, h->params.regularization, d_cov);
   }
-  if (!rc) rc = reduce_sum(h, d_dens, (int)n, idx->seg_start, n_seg, d_sum);
   if (!rc && out_4x4) {
     double* d_out = nullptr;
     NGICP_CUDA(h, dev_alloc(&d_out, n * 16, st));
@@ -711,9 +708,8 @@ int ngicp_batch_covariances(ngicp_handle* p, const void* points, size_t n, size_
   }
   if (!rc && seg_density) {
     std::vector<double> sums(n_seg);
-    NGICP_CUDA(h, cudaMemcpyAsync(sums.data(), d_sum, sizeof(double) * n_seg, cudaMemcpyDeviceToHost, st));
-    NGICP_CUDA(h, cudaStreamSynchronize(st));
-    for (int s = 0; s < n_seg; s++) seg_density[s] = (float)(sums[s] / (double)(seg_offsets[s + 1] - seg_offsets[s]));
+    rc = reduce_sum(h, d_dens, (int)n, idx->seg_start, n_seg, sums.data());
+    for (int s = 0; !rc && s < n_seg; s++) seg_density[s] = (float)(sums[s] / (double)(seg_offsets[s + 1] - seg_offsets[s]));
   }
   NGICP_CUDA(h, cudaStreamSynchronize(st));
   dev_free(d_nbr, st); dev_free(d_dens, st); dev_free(d_sum, st); dev_free(d_cov, st);

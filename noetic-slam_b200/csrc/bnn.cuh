@@ -97,8 +97,10 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
   const float4 o = __ldg(g.seg_origin + seg);
   const float ux = __fsub_rn(qx, o.x), uy = __fsub_rn(qy, o.y), uz = __fsub_rn(qz, o.z);
   int seed_level = -1, sx = 0, sy = 0, sz = 0;   // cell the seed step scanned completely
-  if (!have_hint) {
-    best.d = __int_as_float(0x7f800000); best.i = -1; best.pos = -1;
+  const float hB = h0 * (float)(1 << base);
+  if (!have_hint) { best.d = __int_as_float(0x7f800000); best.i = -1; best.pos = -1; }
+  // a hint farther than half a base cell (the pose moved a lot since it was found) is worth a look at the own cell too
+  if (!have_hint || !(best.d <= 0.25f * hB * hB)) {
     const int c0x = clampi(voxel_coord_unclamped(qx, o.x, inv_h0), 0, kMaxCoord);
     const int c0y = clampi(voxel_coord_unclamped(qy, o.y, inv_h0), 0, kMaxCoord);
     const int c0z = clampi(voxel_coord_unclamped(qz, o.z, inv_h0), 0, kMaxCoord);
@@ -139,7 +141,7 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
   }
   if (!(best.d <= max_sqd)) { best.d = max_sqd; best.i = -1; best.pos = -1; }   // also "no bound at all" (+inf)
   const float r = __fsqrt_ru(best.d) * 1.000001f + margin;   // covers the fp32 rounding of the metric and of the keys
-  const float hL = h0 * (float)(1 << base);
+  const float hL = hB;
   if (sub == 0) { BNN_STAT(0, 1); if (best.i < 0) BNN_STAT(5, 1); if (have_hint) BNN_STAT(4, 1); }
   if (!(r <= 2.0f * hL)) { if (sub == 0) BNN_STAT(1, 1); return false; }                       // also r = +inf / NaN
   const float inv_hL = inv_h0 / (float)(1 << base);          // powers of two: exact

@@ -210,24 +210,6 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
   out[2] = make_float2((float)o.yz, (float)o.zz);
 }
 
-// deterministic per-segment sum: one block per segment
-__global__ void __launch_bounds__(1024) segment_sum_kernel(const double* __restrict__ in, const int* __restrict__ seg_start, double* __restrict__ out) {
-  __shared__ double sm[32];
-  const int b = seg_start[blockIdx.x], e = seg_start[blockIdx.x + 1];
-  double acc = 0.0;
-  for (int i = b + threadIdx.x; i < e; i += blockDim.x) acc += in[i];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = sm[threadIdx.x];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (threadIdx.x == 0) out[blockIdx.x] = acc;
-  }
-}
-
 // ---- layout conversions between the host's CovarianceList order and the device's sorted order ----
 __global__ void __launch_bounds__(256) cov6_to_mat4_kernel(const float4* __restrict__ pts, const float* __restrict__ cov6, int n, double* __restrict__ out16) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,14 +275,6 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
   }
 #undef LAUNCH_COV_K
 #undef LAUNCH_COV
-  count_launch(h);
-  NGICP_CUDA(h, cudaGetLastError());
-  return NGICP_OK;
-}
-
-int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* d_out) {
-  (void)n;
-  segment_sum_kernel<<<n_seg, 1024, 0, h->stream>>>(d_in, seg_start_dev, d_out);
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;

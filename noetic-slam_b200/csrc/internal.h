@@ -120,7 +120,8 @@ int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, i
 // K3. covariance + regularisation from the k-NN table
 int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6);
 // sum of n doubles -> *d_out (device), deterministic
-int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* d_out);
+// deterministic per-segment sums of a device array, delivered to host memory (linearize.cu; blocks until they arrive)
+int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* host_out);
 // covariance layout conversions (host order <-> sorted order)
 int cov6_to_mat4_host_order(Handle* h, const Index* idx, const float* d_cov6, double* d_out16);
 int mat4_host_order_to_cov6(Handle* h, const Index* idx, const double* d_in16, float* d_cov6);

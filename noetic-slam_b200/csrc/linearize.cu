@@ -161,6 +161,20 @@ __device__ __forceinline__ void block_publish(double (*sm)[NT], double* __restri
   }
 }
 
+// Deterministic per-segment sum (the density term of nano_gicp.cc:389): grid = (blocks per segment, segments), same
+// fixed-order reduction and host-mapped result slot as K4b / K5.
+__global__ void __launch_bounds__(kLinThreads) segment_sum_kernel(const double* __restrict__ in, const int* __restrict__ seg_start, double* __restrict__ partials,
+                                                                   unsigned int* __restrict__ counters, ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  __shared__ double wsum[kLinThreads / 32][1];
+  const int begin = __ldg(seg_start + blockIdx.y), end = __ldg(seg_start + blockIdx.y + 1);
+  double acc = 0.0;
+  for (int i = begin + blockIdx.x * kLinThreads + threadIdx.x; i < end; i += gridDim.x * kLinThreads) acc += __ldg(in + i);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][0] = acc;
+  block_publish<1>(wsum, partials, counters, slots, seq);
+}
+
 __device__ __forceinline__ PoseArg load_pose(const PoseArg& p0, const PoseArg* __restrict__ poses) {
   if (!poses) return p0;
   return poses[blockIdx.y];
@@ -468,6 +482,21 @@ static int wait_slot(Handle* h, int n_slots, unsigned long long seq) {
     }
   }
   __sync_synchronize();
+  return NGICP_OK;
+}
+
+int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* host_out) {
+  for (int s0 = 0; s0 < n_seg; s0 += kMaxBatch) {
+    const int ns = std::min(kMaxBatch, n_seg - s0);
+    const int per_seg = std::max(1, n / std::max(n_seg, 1));
+    const int blocks = std::max(1, std::min(std::min(64, kMaxLinBlocks / ns), (per_seg + kLinThreads * 8 - 1) / (kLinThreads * 8)));
+    const unsigned long long seq = ++h->seq;
+    segment_sum_kernel<<<dim3(blocks, ns), kLinThreads, 0, h->stream>>>(d_in, seg_start_dev + s0, h->partials, h->counter, h->slot_dev, seq);
+    count_launch(h);
+    NGICP_CUDA(h, cudaGetLastError());
+    if (int rc = wait_slot(h, ns, seq)) return rc;
+    for (int s = 0; s < ns; s++) host_out[s0 + s] = h->slot_host[s].v[0];
+  }
   return NGICP_OK;
 }
 
