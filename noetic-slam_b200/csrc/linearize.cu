@@ -114,20 +114,24 @@ __device__ __forceinline__ void block_publish(double (*sm)[NT], double* __restri
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // Lane t folds term t over the block partials i = warp, warp + kWarps, ... (fixed order, Neumaier); eight
-  // independent loads are in flight per step because this tail is pure L2 latency. The four per-warp sums are folded
-  // in warp order, written to the host-mapped slot as one row, and published with a single system fence.
-  __shared__ double fin[kWarps][2][32];
+  // Fixed-order fold of the block partials by all 128 threads: thread (term, subset) = (tid % TP, tid / TP) takes
+  // partials subset, subset + SUB, ... (Neumaier, eight independent loads in flight: this tail is pure L2 latency),
+  // then a shuffle tree over the subsets of a warp and a fold over the four warps. One row write to the host-mapped
+  // slot, one system fence, then the sequence number.
+  constexpr int TP = NT <= 1 ? 1 : (NT <= 2 ? 2 : (NT <= 4 ? 4 : (NT <= 8 ? 8 : (NT <= 16 ? 16 : 32))));
+  constexpr int SUB = kLinThreads / TP;
+  __shared__ double fin[kWarps][32];
   const double* all = partials + (size_t)b * gridDim.x * 32;
   const unsigned int nb = gridDim.x;
+  const int term = threadIdx.x % TP, subset = threadIdx.x / TP;
   double s = 0.0, c = 0.0;
-  if (lane < NT) {
-    for (unsigned int i0 = warp; i0 < nb; i0 += kWarps * 8) {
+  if (term < NT) {
+    for (unsigned int i0 = subset; i0 < nb; i0 += SUB * 8) {
       double x[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const unsigned int i = i0 + u * kWarps;
-        x[u] = i < nb ? __ldcg(all + (size_t)i * 32 + lane) : 0.0;
+        const unsigned int i = i0 + u * SUB;
+        x[u] = i < nb ? __ldcg(all + (size_t)i * 32 + term) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -137,21 +141,17 @@ __device__ __forceinline__ void block_publish(double (*sm)[NT], double* __restri
       }
     }
   }
-  fin[warp][0][lane] = s;
-  fin[warp][1][lane] = c;
+  double v = s + c;
+#pragma unroll
+  for (int off = TP; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane < TP) fin[warp][lane] = v;
   __syncthreads();
   if (warp != 0) return;
   if (lane < NT) {
-    double ts = 0.0, tc = 0.0;
+    double t = fin[0][lane];
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) {
-      const double x = fin[w][0][lane];
-      const double y = ts + x;
-      tc += (fabs(ts) >= fabs(x)) ? ((ts - y) + x) : ((x - y) + ts);
-      ts = y;
-      tc += fin[w][1][lane];
-    }
-    slots[b].v[lane] = ts + tc;
+    for (int w = 1; w < kWarps; w++) t += fin[w][lane];
+    slots[b].v[lane] = t;
   }
   __threadfence_system();
   __syncwarp();
@@ -463,8 +463,9 @@ static int g_lin_block_cap = -1;
 int lin_blocks_for(int n) {
   if (g_lin_block_cap < 0) { const char* e = std::getenv("NGICP_LIN_BLOCKS"); g_lin_block_cap = e ? std::atoi(e) : 0; }
   if (g_lin_block_cap > 0) return std::max(1, std::min((n + kLinThreads - 1) / kLinThreads, g_lin_block_cap));
-  const int want = (n + kLinThreads - 1) / kLinThreads;  // one search lane-group per thread slot: latency-bound, spread it wide
-  return std::max(1, std::min(want, kMaxLinBlocks));
+  // two blocks per SM: enough threads in flight for the gathers, few enough partials for a short reduction tail
+  const int want = (n + kLinThreads - 1) / kLinThreads;
+  return std::max(1, std::min(want, 148 * 2));
 }
 
 static int wait_slot(Handle* h, int n_slots, unsigned long long seq) {
