@@ -32,9 +32,38 @@ __global__ void __launch_bounds__(256) index_prep_kernel(unsigned int* lo, unsig
   if (seg_start && i == 0) { seg_start[0] = 0; seg_start[1] = n; }
 }
 
-// per-segment bounding boxes. Warp-aggregated when the whole warp sits in one segment.
+// per-segment bounding boxes. Single-keyframe clouds: registers -> warp shuffles -> shared memory -> six atomics per
+// block. Multi-keyframe clouds: warp-aggregated when the whole warp sits in one segment.
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ xyz, int stride, int n, const int* __restrict__ seg_start, int n_seg,
                                                    unsigned int* __restrict__ lo, unsigned int* __restrict__ hi) {
+  if (n_seg == 1) {
+    unsigned int l[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, u[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const unsigned int o = f2ord(xyz[(size_t)i * stride + a]);
+        l[a] = min(l[a], o); u[a] = max(u[a], o);
+      }
+    }
+    __shared__ unsigned int sl[8][3], su[8][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        l[a] = min(l[a], __shfl_xor_sync(0xffffffffu, l[a], off));
+        u[a] = max(u[a], __shfl_xor_sync(0xffffffffu, u[a], off));
+      }
+      if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5][a] = l[a]; su[threadIdx.x >> 5][a] = u[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      unsigned int ml = sl[0][threadIdx.x], mu = su[0][threadIdx.x];
+      for (int w = 1; w < 8; w++) { ml = min(ml, sl[w][threadIdx.x]); mu = max(mu, su[w][threadIdx.x]); }
+      atomicMin(&lo[threadIdx.x], ml);
+      atomicMax(&hi[threadIdx.x], mu);
+    }
+    return;
+  }
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     const bool valid = i < n;
@@ -193,8 +222,11 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
   return base;
 }
 
-__global__ void __launch_bounds__(256) table_insert_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta,
-                                                           CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy) {
+// Every sorted position opens the cells whose first point it is and closes the cells whose last point it is; both find
+// the cell's slot by find-or-insert (atomicCAS on the key), so one pass over the sorted keys fills start AND end:
+// whichever of the two threads arrives first claims the slot, the fields they write are disjoint.
+__global__ void __launch_bounds__(256) table_build_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta,
+                                                          CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy) {
   __shared__ int s_base;
   if (threadIdx.x == 0) {
     unsigned int total;
@@ -206,34 +238,19 @@ __global__ void __launch_bounds__(256) table_insert_kernel(const unsigned long l
   if (j >= n) return;
   const int base = s_base;
   const unsigned long long k = keys[j];
-  const int d = j == 0 ? kNumLevels : diff_levels(k, keys[j - 1]);
+  const int d_open = j == 0 ? kNumLevels : diff_levels(k, keys[j - 1]);
+  const int d_close = j == n - 1 ? kNumLevels : diff_levels(k, keys[j + 1]);
+  const int d = max(d_open, d_close);
   for (int L = base; L < d; L++) {
     const unsigned long long ck = cell_key(k, L);
     uint32_t h = hash64(ck) & mask;
     for (;;) {
       const unsigned long long prev = atomicCAS(&table[h].key, kEmptyKey, ck);
-      if (prev == kEmptyKey) { table[h].start = (uint32_t)j; break; }
+      if (prev == kEmptyKey || prev == ck) break;
       h = (h + 1) & mask;
     }
-  }
-}
-
-__global__ void __launch_bounds__(256) table_close_kernel(const unsigned long long* __restrict__ keys, int n, const GridMeta* __restrict__ meta,
-                                                          CellSlot* __restrict__ table, uint32_t mask) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int base = meta->base_level;
-  const unsigned long long k = keys[j];
-  const int d = j == n - 1 ? kNumLevels : diff_levels(k, keys[j + 1]);
-  for (int L = base; L < d; L++) {
-    const unsigned long long ck = cell_key(k, L);
-    uint32_t h = hash64(ck) & mask;
-    for (;;) {
-      const unsigned long long cur = table[h].key;
-      if (cur == ck) { table[h].end = (uint32_t)(j + 1); break; }
-      if (cur == kEmptyKey) break;  // cannot happen: every closing cell was opened by table_insert_kernel
-      h = (h + 1) & mask;
-    }
+    if (L < d_open) table[h].start = (uint32_t)j;
+    if (L < d_close) table[h].end = (uint32_t)(j + 1);
   }
 }
 
@@ -323,7 +340,7 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   const int nb = (n + tpb - 1) / tpb;
   const int n_hist = passes * kSortRadix;
   index_prep_kernel<<<(std::max(3 * n_seg, n_hist) + 255) / 256, 256, 0, s>>>(lo, hi, n_seg, sort_scratch, n_hist, n_seg == 1 ? idx->seg_start : nullptr, n);
-  bbox_kernel<<<std::min(nb, 148 * 8), tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, lo, hi);
+  bbox_kernel<<<std::min(nb, n_seg == 1 ? 148 : 148 * 8), tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, lo, hi);
   count_launch(h, 2);
   if (n_seg > 1) {
     grid_meta_kernel<<<1, 256, 0, s>>>(lo, hi, n_seg, idx->seg_origin, idx->meta);
@@ -339,9 +356,8 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
     keys_sorted = idx->keys;
   }
   gather_levels_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, keys_sorted, idx->pts, idx->inv, idx->meta);
-  table_insert_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, cap / 2, 2);
-  table_close_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask);
-  count_launch(h, 3);
+  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, cap / 2, 2);
+  count_launch(h, 2);
   IDX_CUDA(cudaGetLastError());
   dev_free(scratch, s);
 #undef IDX_CUDA

@@ -5,8 +5,8 @@
 // Per pass:   count   : per-tile digit counts            counts[digit][tile]
 //             scanrow : exclusive scan of every digit row over tiles
 //             scatter : warp-synchronous stable ranking (match_any) + scatter
-// A tile is 256 threads x 8 keys; warp w of a tile owns the contiguous chunk of 256 keys
-// [w*256, (w+1)*256) so that (tile, warp, round, lane) order == input order, which makes the
+// A tile is 256 threads x ITEMS keys (8, or 2 for small inputs); warp w of a tile owns the contiguous chunk of 32*ITEMS keys
+// [w*32*ITEMS, (w+1)*32*ITEMS) so that (tile, warp, round, lane) order == input order, which makes the
 // scatter stable. All global reads are coalesced 256-byte warp rows.
 #include "radix_sort.cuh"
 
@@ -28,19 +28,22 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const unsigned long
     if (h[i]) atomicAdd(&digit_hist[i], h[i]);
 }
 
+// counts layout: [tile][digit] when the scatter kernel sums the earlier tiles itself (few tiles), [digit][tile] when
+// sort_scan_rows_kernel turns every digit row into an exclusive prefix first (many tiles)
+template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) sort_count_kernel(const unsigned long long* __restrict__ keys, int n, int shift,
-                                                                 uint32_t* __restrict__ counts, int nblocks) {
+                                                                 uint32_t* __restrict__ counts, int nblocks, int rows_scanned) {
   __shared__ uint32_t h[kSortRadix];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const int base = blockIdx.x * kSortTile;
+  const int base = blockIdx.x * (kSortThreads * ITEMS);
 #pragma unroll
-  for (int r = 0; r < kSortItems; r++) {
+  for (int r = 0; r < ITEMS; r++) {
     const int i = base + r * kSortThreads + threadIdx.x;
     if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & (kSortRadix - 1))], 1u);
   }
   __syncthreads();
-  counts[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  counts[rows_scanned ? threadIdx.x * nblocks + blockIdx.x : blockIdx.x * kSortRadix + threadIdx.x] = h[threadIdx.x];
 }
 
 // grid = 256 blocks (one digit row each), 256 threads; exclusive scan of counts[d][0..nblocks)
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(256) sort_scan_rows_kernel(uint32_t* __restric
   }
 }
 
+template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                    unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ digit_total,
@@ -92,18 +96,24 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
     }
     uint32_t row = 0;  // keys with this digit in earlier tiles
     if (rows_scanned) row = counts[threadIdx.x * nblocks + blockIdx.x];
-    else for (int b = 0; b < (int)blockIdx.x; b++) row += counts[threadIdx.x * nblocks + b];
+    else {
+      int b = 0;
+      for (; b + 4 <= (int)blockIdx.x; b += 4)   // coalesced rows, four loads in flight
+        row += (counts[b * kSortRadix + threadIdx.x] + counts[(b + 1) * kSortRadix + threadIdx.x]) +
+               (counts[(b + 2) * kSortRadix + threadIdx.x] + counts[(b + 3) * kSortRadix + threadIdx.x]);
+      for (; b < (int)blockIdx.x; b++) row += counts[b * kSortRadix + threadIdx.x];
+    }
     const uint32_t start = digit_base[threadIdx.x] - v;
     __syncthreads();
     digit_base[threadIdx.x] = start + row;
   }
   __syncthreads();
 
-  const int chunk0 = blockIdx.x * kSortTile + warp * (32 * kSortItems);
-  unsigned long long key[kSortItems];
-  int dig[kSortItems];
+  const int chunk0 = blockIdx.x * (kSortThreads * ITEMS) + warp * (32 * ITEMS);
+  unsigned long long key[ITEMS];
+  int dig[ITEMS];
 #pragma unroll
-  for (int r = 0; r < kSortItems; r++) {
+  for (int r = 0; r < ITEMS; r++) {
     const int i = chunk0 + r * 32 + lane;
     const bool valid = i < n;
     key[r] = valid ? keys_in[i] : 0ull;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
   }
   // phase 1: per-warp digit counts
 #pragma unroll
-  for (int r = 0; r < kSortItems; r++) {
+  for (int r = 0; r < ITEMS; r++) {
     const unsigned m = __match_any_sync(0xffffffffu, dig[r]);
     if (dig[r] < kSortRadix && lane == __ffs(m) - 1) warp_cnt[warp][dig[r]] += __popc(m);
     __syncwarp();
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
   __syncthreads();
   // phase 2: stable rank + scatter
 #pragma unroll
-  for (int r = 0; r < kSortItems; r++) {
+  for (int r = 0; r < ITEMS; r++) {
     const unsigned m = __match_any_sync(0xffffffffu, dig[r]);
     const bool valid = dig[r] < kSortRadix;
     uint32_t pos = 0;
@@ -165,14 +175,20 @@ int radix_sort_pairs(unsigned long long* keys_a, uint32_t* vals_a, unsigned long
     sort_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, low_bit, passes, digit_hist);
     launches += 1;
   }
-  const bool scan_rows = nblocks > 64;   // few tiles: the scatter kernel sums the earlier tiles itself
+  const bool scan_rows = nblocks > 256;   // few tiles: the scatter kernel sums the earlier tiles itself
+  const int items = sort_items_for(n);
   unsigned long long* kin = keys_a; uint32_t* vin = vals_a;
   unsigned long long* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; p++) {
     const int shift = low_bit + p * kSortRadixBits;
-    sort_count_kernel<<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks);
-    if (scan_rows) sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
-    sort_scatter_kernel<<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+    if (items == 2) {
+      sort_count_kernel<2><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
+      sort_scatter_kernel<2><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+    } else {
+      sort_count_kernel<8><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
+      if (scan_rows) sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
+      sort_scatter_kernel<8><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+    }
     launches += scan_rows ? 3 : 2;
     unsigned long long* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

@@ -10,12 +10,11 @@ namespace ngicp {
 constexpr int kSortRadixBits = 8;
 constexpr int kSortRadix = 1 << kSortRadixBits;
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;                                  // keys per thread
-constexpr int kSortTile = kSortThreads * kSortItems;           // keys per block
-
-inline int sort_num_blocks(int n) { return (n + kSortTile - 1) / kSortTile; }
+// keys per thread: 2 for small inputs (a 65,536-point scan becomes 128 tiles instead of 32 and reaches most SMs), 8 otherwise
+inline int sort_items_for(int n) { return n <= 131072 ? 2 : 8; }
+inline int sort_num_blocks(int n) { const int tile = kSortThreads * sort_items_for(n); return (n + tile - 1) / tile; }
 inline int sort_num_passes(int nbits) { return (nbits + kSortRadixBits - 1) / kSortRadixBits; }
-// scratch (uint32 elements): per-pass digit starts [passes*256] + per-block counts [256*nblocks]
+// scratch (uint32 elements): per-pass digit totals [passes*256] + per-tile digit counts [256*tiles]
 inline size_t sort_scratch_elems(int n, int nbits) {
   return (size_t)sort_num_passes(nbits) * kSortRadix + (size_t)kSortRadix * sort_num_blocks(n) + 64;
 }
