@@ -203,6 +203,55 @@ struct TopK {
   }
 };
 
+// The same list as packed 64-bit keys (distance bits << 32 | original index): squared distances are non-negative, so
+// the unsigned integer order of the keys IS the (distance, index) order — no separate tie path, and two sorted lists
+// merge with a plain compare-exchange network. Used for the per-lane partial lists of the warp search.
+template <int K>
+struct KeyList {
+  static constexpr int KP = K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : (K <= 32 ? 32 : 64)))));   // network size
+  unsigned long long k[KP];
+  static constexpr unsigned long long kEmpty = (0x7f800000ull << 32) | 0xffffffffull;   // (+inf, -1)
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < KP; i++) k[i] = kEmpty;
+  }
+  __device__ __forceinline__ float worst() const { return __uint_as_float((unsigned int)(k[K - 1] >> 32)); }
+  __device__ __forceinline__ void offer(float dn, int pn) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(dn) << 32) | (unsigned int)pn;
+    if (key >= k[K - 1]) return;
+#pragma unroll
+    for (int i = K - 1; i > 0; i--) {
+      const bool lti = k[i] < key, ltm = k[i - 1] < key;
+      k[i] = lti ? k[i] : (ltm ? key : k[i - 1]);
+    }
+    k[0] = k[0] < key ? k[0] : key;
+  }
+  // Both lanes of an xor pair end up with the K smallest keys of their two sorted lists, sorted.
+  __device__ __forceinline__ void merge_with_partner(int off) {
+    unsigned long long o[KP];
+#pragma unroll
+    for (int i = 0; i < KP; i++) o[i] = __shfl_xor_sync(0xffffffffu, k[i], off);
+#pragma unroll
+    for (int i = 0; i < KP; i++) k[i] = k[i] < o[KP - 1 - i] ? k[i] : o[KP - 1 - i];   // KP smallest, bitonic
+#pragma unroll
+    for (int s = KP / 2; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int i = 0; i < KP; i++) {
+        if ((i & s) == 0) {
+          const unsigned long long a = k[i], b = k[i + s];
+          const bool lt = a < b;
+          k[i] = lt ? a : b;
+          k[i + s] = lt ? b : a;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void store(TopK<K>& t) const {
+#pragma unroll
+    for (int i = 0; i < K; i++) { t.d[i] = __uint_as_float((unsigned int)(k[i] >> 32)); t.p[i] = (int)(unsigned int)k[i]; }
+  }
+};
+
 // Slow-path list for k > 32 (the reference accepts any k): same ordering, runtime capacity, lives
 // in local memory.
 template <int KMAX>

@@ -318,75 +318,53 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           if ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1)) && bp >= 0 && bd <= best.worst()) best.offer(bd, bp);
         }
       })
-    } else if ((long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M) {
-      // heavy tail: few member queries, many candidates -> all 32 lanes split the candidates of one query
-      unsigned rem = mem_mask;
-      while (rem) {
-        const int mi = __ffs(rem) - 1;
-        rem &= ~(grp_mask << (mi & ~(LPQ - 1)));
-        const float mx = __shfl_sync(FULL, qx, mi), my = __shfl_sync(FULL, qy, mi), mz = __shfl_sync(FULL, qz, mi);
-        TK part;
-        part.reset();
+    } else {
+      // k > 1. One scan loop and one merge for both ways of sharing the staged candidates:
+      //   shared : every member query is scanned by its own LPQ lanes (width LPQ, one round)
+      //   heavy  : few member queries, many candidates -> all 32 lanes split the candidates of one query at a time
+      // Each lane keeps a private sorted list of packed (distance, index) keys over its share; the lists of the `width`
+      // lanes are then merged by log2(width) bitonic steps (exchange with the xor partner, keep the K smallest of the
+      // two sorted lists as a bitonic sequence, re-sort it with the half-cleaner network). Deliberately ONE code site
+      // for the insertion and ONE for the merge: this kernel used to be 138 KB of SASS and stalled on instruction fetch.
+      const bool heavy = LPQ == 1 ? false : (long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M;
+      if (LPQ == 1) {
         WKNN_FOR_CHUNKS({
-          for (int e = lane; e < nch; e += 32) {
-            const float4 p = P[e];
-            const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
-            if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
+          if (member) {
+#pragma unroll 4
+            for (int e = 0; e < nch; e++) {
+              const float4 p = P[e];
+              const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
+              if (d <= best.worst()) best.offer(d, __float_as_int(p.w));
+            }
           }
         })
-        const bool mine = (lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1));
-#pragma unroll
-        for (int rr = 0; rr < TK::kK; rr++) {   // merge the 32 private lists: K rounds of "smallest head wins"
-          float gd = part.d[0];
-          int gp = part.p[0];
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(FULL, gd, off);
-            const int op = __shfl_xor_sync(FULL, gp, off);
-            if (TK::before(od, op, gd, gp)) { gd = od; gp = op; }
-          }
-          if (gp >= 0 && gp == part.p[0]) part.pop_front();
-          if (mine) best.append_shift(gd, gp);   // K appends leave the list in ascending order
-        }
-      }
-    } else if (LPQ == 1) {
-      WKNN_FOR_CHUNKS({
-        if (member) {
-#pragma unroll 4
-          for (int e = 0; e < nch; e++) {
-            const float4 p = P[e];
-            const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= best.worst()) best.offer(d, __float_as_int(p.w));
-          }
-        }
-      })
-    } else {
-      // shared mode, LPQ lanes per query: lane `sub` takes candidates sub, sub+LPQ, ... into a private list,
-      // then the LPQ lists of a query are merged by K rounds of group-argmin (xor shuffles inside the group)
-      TK part;
-      part.reset();
-      WKNN_FOR_CHUNKS({
-        if (member) {
+      } else {
+        const int width = heavy ? 32 : LPQ;
+        const int s0 = lane & (width - 1);
+        unsigned rem = heavy ? mem_mask : 1u;
+        while (rem) {                                  // warp-uniform
+          const int mi = __ffs(rem) - 1;               // heavy: first lane of the member query of this round
+          rem = heavy ? (rem & ~(grp_mask << (mi & ~(LPQ - 1)))) : 0u;
+          const float mx = heavy ? __shfl_sync(FULL, qx, mi) : qx;
+          const float my = heavy ? __shfl_sync(FULL, qy, mi) : qy;
+          const float mz = heavy ? __shfl_sync(FULL, qz, mi) : qz;
+          const bool scan = heavy || member;
+          KeyList<TK::kK> part;
+          part.reset();
+          WKNN_FOR_CHUNKS({
+            if (scan) {
 #pragma unroll 2
-          for (int e = sub; e < nch; e += LPQ) {
-            const float4 p = P[e];
-            const float d = sqdist_ref(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
-          }
+              for (int e = s0; e < nch; e += width) {
+                const float4 p = P[e];
+                const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
+                if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
+              }
+            }
+          })
+          for (int off = 1; off < width; off <<= 1) part.merge_with_partner(off);
+          const bool take = heavy ? ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1))) : member;
+          if (take) part.store(best);
         }
-      })
-#pragma unroll
-      for (int rr = 0; rr < TK::kK; rr++) {
-        float gd = part.d[0];
-        int gp = part.p[0];
-#pragma unroll
-        for (int off = LPQ / 2; off > 0; off >>= 1) {
-          const float od = __shfl_xor_sync(FULL, gd, off);
-          const int op = __shfl_xor_sync(FULL, gp, off);
-          if (TK::before(od, op, gd, gp)) { gd = od; gp = op; }
-        }
-        if (gp >= 0 && gp == part.p[0]) part.pop_front();
-        if (member) best.append_shift(gd, gp);
       }
     }
 
