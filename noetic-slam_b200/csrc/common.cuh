@@ -226,6 +226,31 @@ struct KeyList {
     }
     k[0] = k[0] < key ? k[0] : key;
   }
+  static __device__ __forceinline__ unsigned long long make_key(float d, int p) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)p;
+  }
+  // full bitonic sorting network over the KP slots (static indices only): used once per scan to seed the list from the
+  // first KP candidates, which is several times cheaper than KP insertions
+  __device__ __forceinline__ void sort_all() {
+#pragma unroll
+    for (int size = 2; size <= KP; size <<= 1) {
+#pragma unroll
+      for (int stride = size / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int i = 0; i < KP; i++) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const bool up = (i & size) == 0;
+            const unsigned long long a = k[i], b = k[j];
+            const bool sw = up ? (b < a) : (a < b);
+            k[i] = sw ? b : a;
+            k[j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ float dist_at(int i) const { return __uint_as_float((unsigned int)(k[i] >> 32)); }
   // Both lanes of an xor pair end up with the K smallest keys of their two sorted lists, sorted.
   __device__ __forceinline__ void merge_with_partner(int off) {
     unsigned long long o[KP];

@@ -350,14 +350,37 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           const float mz = heavy ? __shfl_sync(FULL, qz, mi) : qz;
           const bool scan = heavy || member;
           KeyList<TK::kK> part;
-          part.reset();
+          // The private lists together prove a bound on the final k-th distance long before any one of them is full:
+          // when every lane of the query holds Q entries and width * Q >= K, at least K candidates are known at or
+          // below the largest of the lanes' Q-th entries, so nothing farther can make the final list.
+          constexpr int kQs = (TK::kK + LPQ - 1) / LPQ - 1;          // shared: LPQ lanes per query
+          constexpr int kQh = (TK::kK + 31) / 32 - 1;                // heavy: 32 lanes per query
+          float lim = __int_as_float(0x7f800000);
           WKNN_FOR_CHUNKS({
+            int e_first = s0;
+            if (c0 == 0) {
+              // seed: the first KP candidates of this lane's share, sorted by a network instead of inserted one by one
+#pragma unroll
+              for (int i = 0; i < KeyList<TK::kK>::KP; i++) {
+                const int e = s0 + i * width;
+                const float4 p = P[min(e, nch - 1)];
+                const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
+                part.k[i] = (scan && e < nch) ? KeyList<TK::kK>::make_key(d, __float_as_int(p.w)) : KeyList<TK::kK>::kEmpty;
+              }
+              part.sort_all();
+              e_first = s0 + KeyList<TK::kK>::KP * width;
+            }
+            {
+              float b = heavy ? part.dist_at(kQh) : part.dist_at(kQs);
+              for (int off = 1; off < width; off <<= 1) b = fmaxf(b, __shfl_xor_sync(FULL, b, off));
+              lim = fminf(lim, b);
+            }
             if (scan) {
 #pragma unroll 2
-              for (int e = s0; e < nch; e += width) {
+              for (int e = e_first; e < nch; e += width) {
                 const float4 p = P[e];
                 const float d = sqdist_ref(mx, my, mz, p.x, p.y, p.z);
-                if (d <= part.worst()) part.offer(d, __float_as_int(p.w));
+                if (d <= fminf(lim, part.worst())) part.offer(d, __float_as_int(p.w));
               }
             }
           })
