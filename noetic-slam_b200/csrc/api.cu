@@ -59,15 +59,35 @@ int ensure_stage(Handle* h, size_t bytes) {
   return NGICP_OK;
 }
 
-// host AoS (xyz at floats 0..2 of every `stride_bytes` record) -> packed float3 on the device
-int upload_xyz(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz) {
+// host AoS (xyz at floats 0..2 of every `stride_bytes` record) -> device. Pageable memory is packed into the pinned
+// staging buffer first (3 floats per point on the device). Page-locked memory (cudaHostAlloc / cudaHostRegister) with
+// a stride of at most 32 bytes is copied as it is, asynchronously and without touching it on the CPU; the kernels
+// read it with its stride (*stride_floats). Such a buffer must stay unchanged until the next call that synchronises
+// (covariances with a density, align) — the reference keeps a pointer to the caller's cloud for just as long.
+int upload_xyz(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats = nullptr) {
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(h, NGICP_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
+  if (stride_floats) {
+    *stride_floats = 3;
+    cudaPointerAttributes at;
+    const cudaError_t q = cudaPointerGetAttributes(&at, points);
+    if (q != cudaSuccess) cudaGetLastError();   // plain pageable memory on older drivers: not an error
+    if (q == cudaSuccess && at.type == cudaMemoryTypeHost && stride_bytes <= 32) {
+      NGICP_CUDA(h, dev_alloc(d_xyz, n * (stride_bytes / 4), h->stream));
+      NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz, points, n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+      *stride_floats = (int)(stride_bytes / 4);
+      return NGICP_OK;
+    }
+  }
   if (int rc = ensure_stage(h, n * 12)) return rc;
   float* st = static_cast<float*>(h->stage_host);
   const char* src = static_cast<const char*>(points);
-  for (size_t i = 0; i < n; i++) {
-    const float* p = reinterpret_cast<const float*>(src + i * stride_bytes);
-    st[3 * i] = p[0]; st[3 * i + 1] = p[1]; st[3 * i + 2] = p[2];
+  if (stride_bytes == 12) {
+    std::memcpy(st, src, n * 12);
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      const float* p = reinterpret_cast<const float*>(src + i * stride_bytes);
+      st[3 * i] = p[0]; st[3 * i + 1] = p[1]; st[3 * i + 2] = p[2];
+    }
   }
   NGICP_CUDA(h, dev_alloc(d_xyz, n * 3, h->stream));
   NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz, st, n * 12, cudaMemcpyHostToDevice, h->stream));
@@ -439,9 +459,10 @@ int ngicp_set_input(ngicp_handle* p, int which, const void* points, size_t n, si
   if (!points || n == 0) return fail(h, NGICP_ERR_INVALID, "ngicp_set_input: empty cloud");
   if (int rc = use_device(h)) return rc;
   float* d_xyz = nullptr;
-  if (int rc = upload_xyz(h, points, n, stride_bytes, &d_xyz)) return rc;
+  int stride = 3;
+  if (int rc = upload_xyz(h, points, n, stride_bytes, &d_xyz, &stride)) return rc;
   Index* idx = nullptr;
-  const int rc = build_index(h, d_xyz, 3, (int)n, nullptr, 1, &idx);
+  const int rc = build_index(h, d_xyz, stride, (int)n, nullptr, 1, &idx);
   dev_free(d_xyz, h->stream);
   if (rc) return rc;
   return swap_in_index(h, which, idx);
