@@ -81,6 +81,16 @@ def make_workload(seed: int):
     return tgt, bounds, scans
 
 
+def ncu_traffic(name):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            v = json.load(f).get(name)
+        return None if v is None else float(v)
+    except (OSError, ValueError):
+        return None
+
+
 def configure(g):
     import scenarios as S
     return S.configure(g, k=K_CORR, max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)   # cfg/params.yaml:57-63
@@ -293,10 +303,10 @@ def run_gpu(args, rank, local_rank, world):
                   "K4b_linearize": t["linearize_ms"], "K5_error": t["error_ms"]}
     dominant = max(step_share, key=step_share.get)
     kernels = {k: {"ms_per_launch": ms, "algorithmic_bytes": b, "GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None,
-                   "share_of_step": step_share[k] / max(sum(step_share.values()), 1e-9)} for k, (ms, b) in per.items()}
+                   "share_of_step": step_share[k] / max(sum(step_share.values()), 1e-9), "ncu_dram_bytes": ncu_traffic(k)} for k, (ms, b) in per.items()}
     dm, db = per[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": db / (dm * 1e-3) / 1e9, "peak": hbm["gbs"], "unit": "GB/s",
-                "frac": db / (dm * 1e-3) / 1e9 / hbm["gbs"], "traffic": None, "peak_source": hbm["source"],
+                "frac": db / (dm * 1e-3) / 1e9 / hbm["gbs"], "traffic": ncu_traffic(dominant), "peak_source": hbm["source"],
                 "note": "single-scan launches are L2/latency-bound (5 MB per launch); the HBM bar applies to the bulk numbers below"}
 
     # ---- judged bulk numbers: K3 on a bulk keyframe batch (BASELINE config 3 shape, bounded to 64 keyframes per GPU)
@@ -354,7 +364,7 @@ def bulk_covariance(g, scans, hbm, n_keyframes=64):
     dev_ms = out["index_ms"] + out["knn_ms"] + out["covariance_ms"]
     out["covariance_mpts_s_device"] = n / (dev_ms * 1e-3) / 1e6
     k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
-    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": None,
+    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": ncu_traffic("bulk_K3"),
                           "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
     return out
 
@@ -383,7 +393,7 @@ def bulk_linearize(g, scans, hbm, n_scans=64):
     g.enableTiming(False)
     n = len(pts)
     k4b = BYTES["K4b_lin_per_src_pt"] * n / (out["batch_linearize_ms"] * 1e-3) / 1e9
-    out["roofline_K4b"] = {"bound": "hbm", "achieved": k4b, "peak": hbm["gbs"], "unit": "GB/s", "frac": k4b / hbm["gbs"], "traffic": None,
+    out["roofline_K4b"] = {"bound": "hbm", "achieved": k4b, "peak": hbm["gbs"], "unit": "GB/s", "frac": k4b / hbm["gbs"], "traffic": ncu_traffic("bulk_K4b"),
                            "algorithmic_bytes_per_pt": BYTES["K4b_lin_per_src_pt"], "peak_source": hbm["source"],
                            "note": "unmatched points move 20 B instead of 84 B; bytes are counted as if every point matched"}
     out["batch_scans_per_s_linearize_only"] = n_scans / ((out["batch_correspond_ms"] + out["batch_linearize_ms"]) * 1e-3)
