@@ -233,6 +233,52 @@ def test_max_correspondence_distance_is_honoured():
     assert (corr >= 0).all()
 
 
+def test_correspondences_exact_along_a_pose_sequence_with_stale_hints():
+    """The bounded search seeds every query with its previous correspondence; whatever the pose does in between
+    (large jumps make the hints useless or wrong, small steps make them tight), every call must return the oracle's
+    nearest neighbours exactly."""
+    g, o = _pair(11, w=256)
+    poses = [np.eye(4), synth.se3((0.4, -0.3, 0.1), (8.0, -3.0, 2.0)), synth.se3((0.41, -0.3, 0.1), (8.1, -3.0, 2.0)),
+             synth.se3((-0.6, 0.5, -0.2), (-15.0, 4.0, 1.0)), np.eye(4), synth.se3((0.001, 0.0, 0.0), (0.0, 0.01, 0.0)),
+             synth.se3((30.0, 0.0, 0.0), (0.0, 0.0, 0.0)), np.eye(4)]
+    for thr in (0.5, 3.0):
+        g.setMaxCorrespondenceDistance(thr); o.setMaxCorrespondenceDistance(thr)
+        for T in poses:
+            corr, sqd, _ = g.update_correspondences(T)
+            co, so, _ = o.update_correspondences(T)
+            assert (corr == co).all()
+            v = corr >= 0
+            assert (sqd[v] == so[v]).all()
+            e, H, b = g.linearize(T)      # the linearisation consumes the same correspondences
+            eo, Ho, bo = o.linearize(T)
+            assert g.num_correspondences == o.num_correspondences
+            if eo != 0:
+                assert abs(e - eo) < 1e-6 * abs(eo)
+
+
+def test_correspondences_with_duplicate_target_points_break_ties_by_index():
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-2, 2, (3000, 3)).astype(np.float32)
+    tgt = np.concatenate([base, base[::3], base[::7]])            # exact duplicates at different indices
+    src = (base[::2] + rng.normal(0, 0.01, base[::2].shape)).astype(np.float32)
+    src[::5] = base[::2][::5]                                     # some queries sit exactly on a duplicated point
+    g = S.configure(ngicp.NanoGICP(0), k=16)
+    o = S.configure(oracle.OracleGICP("port"), k=16)
+    for x in (g, o):
+        x.setInputSource(src); x.setInputTarget(tgt)
+        x.calculateSourceCovariances(); x.calculateTargetCovariances()
+    for T in (np.eye(4), synth.se3((0.02, 0.0, -0.01), (0.5, 0.0, 0.0))):
+        corr, sqd, _ = g.update_correspondences(T)
+        co, so, _ = o.update_correspondences(T)
+        v = corr >= 0
+        assert ((corr >= 0) == (co >= 0)).all() and (sqd[v] == so[v]).all()
+        # the oracle's k-d tree keeps visit order on exact ties; the documented order here is the smallest index
+        tie_free = tgt[corr[v]] == tgt[co[v]]
+        assert tie_free.all()
+        dup_first = np.array([np.flatnonzero((tgt == tgt[c]).all(1))[0] for c in corr[v][:200]])
+        assert (corr[v][:200] == dup_first).all()
+
+
 # ----------------------------------------------------------------------------------- align
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_align_pose_and_iterations_vs_oracle(seed):
