@@ -313,6 +313,7 @@ def run_gpu(args, rank, local_rank, world):
     #      and K4b (fused linearisation) on a batch of 64 scans against the resident submap
     bulk = bulk_covariance(g, scans, hbm)
     bulk.update(bulk_linearize(g, scans, hbm))
+    bulk.update(prefilter_probe(g, pinned, h_scans, world == 1))
 
     # ---- CPU baseline beside it (bounded sample, all host cores) — rank 0 at N=1 only
     cpu = None
@@ -366,6 +367,31 @@ def bulk_covariance(g, scans, hbm, n_keyframes=64):
     k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
     out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": ncu_traffic("bulk_K3"),
                           "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
+    return out
+
+
+def prefilter_probe(g, pinned, h_scans, with_cpu):
+    """CropBox -> VoxelGrid -> setInputSource on the device for one raw 65,536-point scan (host buffer in,
+    index out), beside the same two PCL filters restated on one CPU core (PCL's filters are single-threaded)."""
+    crop = ([-1.0] * 3, [1.0] * 3, True)        # cfg/params.yaml: crop size 1.0
+    leaf = (0.25, 0.25, 0.25)
+    ts = []
+    n_out = 0
+    for i in range(8):
+        hs = pinned[i % len(pinned)].numpy()
+        hs[:] = h_scans[i % len(h_scans)]
+        t0 = time.perf_counter()
+        n_out = len(g.setInputSourceFiltered(hs, crop=crop, leaf=leaf))
+        ts.append(time.perf_counter() - t0)
+    out = {"prefilter_points_in": N_SCAN, "prefilter_points_out": int(n_out), "prefilter_ms_crop_voxel_index": 1e3 * float(np.median(ts[2:]))}
+    if with_cpu:
+        import oracle
+        oc = oracle.CropBox(); oc.setNegative(True); oc.setMin(crop[0]); oc.setMax(crop[1])
+        ov = oracle.VoxelGrid(); ov.setLeafSize(*leaf)
+        t0 = time.perf_counter()
+        for i in range(5):
+            oc.setInputCloud(h_scans[i % len(h_scans)]); ov.setInputCloud(oc.filter()); ov.filter()
+        out["prefilter_cpu_ms_crop_voxel"] = 1e3 * (time.perf_counter() - t0) / 5
     return out
 
 

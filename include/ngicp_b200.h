@@ -175,6 +175,19 @@ int ngicp_keyframe_release(ngicp_handle* h, ngicp_keyframe* kf);
 int ngicp_keyframe_download(ngicp_handle* h, const ngicp_keyframe* kf, float* xyz, double* cov_4x4);
 int ngicp_submap_assemble(ngicp_handle* h, ngicp_keyframe* const* kfs, int n_kfs);
 
+/* ---- scan pre-filters on the device --------------------------------------------------------
+ * The two PCL filters DLIO runs right before setInputSource, in DLIO's order: pcl::CropBox (reference
+ * src/dlio/src/dlio/odom.cc:114-116 configure, :500-502 apply) then pcl::VoxelGrid (odom.cc:118, :575-584), xyz only.
+ *   crop_min / crop_max  box corners, both NULL = no crop; crop_negative != 0 keeps the points OUTSIDE the box (DLIO)
+ *   leaf                 voxel size per axis, NULL = no voxel grid. Output = fp32 centroid of every occupied voxel in
+ *                        ascending PCL voxel-index order (sum in ascending input order / count)
+ *   set_as               0 / 1: the filtered cloud also becomes the handle's SOURCE / TARGET cloud without leaving the
+ *                        device (replaces setInputSource(filtered cloud)); -1: filter only
+ *   out_xyz              optional host buffer, capacity n x 3 floats; *n_out = points that survived
+ * Non-finite points are dropped (pcl::removeNaNFromPointCloud, odom.cc:496-498). */
+int ngicp_filter_scan(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes, const float crop_min[3], const float crop_max[3],
+                      int crop_negative, const float leaf[3], int set_as, float* out_xyz, size_t* n_out);
+
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
 typedef struct ngicp_timings {
   float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */

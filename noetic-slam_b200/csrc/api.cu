@@ -450,6 +450,9 @@ int swap_in_index(Handle* h, int which, Index* idx) {
   return NGICP_OK;
 }
 int select_device(Handle* h) { return use_device(h); }
+int upload_points(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats) {
+  return upload_xyz(h, points, n, stride_bytes, d_xyz, stride_floats);
+}
 }  // namespace ngicp
 }  // extern "C++"
 

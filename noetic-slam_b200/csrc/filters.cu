@@ -1,0 +1,401 @@
+// Scan pre-filters on the device (SURVEY.md §8f "next" row 2): the two PCL filters DLIO applies right before
+// setInputSource — pcl::CropBox (reference src/dlio/src/dlio/odom.cc:114-116 configure, :500-502 apply) and
+// pcl::VoxelGrid (odom.cc:118 configure, :575-584 apply). PCL (>= 1.10.0, apt libpcl-dev) is a third-party dependency
+// that is not vendored in the reference; the algorithm restated here is PCL 1.10's
+// filters/impl/crop_box.hpp (applyFilter) and filters/impl/voxel_grid.hpp (applyFilter, downsample_all_data_ = true,
+// min_points_per_voxel_ = 0), xyz only:
+//   CropBox   keep a finite point iff (inside box) != negative, inside = !(p < min || p > max) on any axis; order kept.
+//   VoxelGrid min/max of the finite points -> min_b = floor(min * inv_leaf), div_b = max_b - min_b + 1 ->
+//             idx = ijk0 + ijk1 * div_b0 + ijk2 * div_b0 * div_b1 with ijk = int(floor(p * inv_leaf) - float(min_b))
+//             (all fp32) -> sort by idx -> one output per occupied voxel, in ascending idx order, = fp32 sum of its
+//             points / count. If the voxel count overflows int32 PCL warns and returns the input unchanged; so do we.
+// PCL sorts with std::sort, whose order inside a voxel is unspecified, so its fp32 sums are only defined up to
+// rounding; this implementation (and the oracle) fix the order to ascending input index (stable sort).
+// Same machinery as K1: fused key + digit-histogram kernel, the hand-written stable LSD radix sort, then one pass over
+// the sorted keys. Everything stays in HBM; only the output count comes back (host-mapped slot).
+#include <algorithm>
+#include <vector>
+
+#include "internal.h"
+#include "linearize.cuh"
+#include "radix_sort.cuh"
+
+namespace ngicp {
+
+int upload_points(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats);   // api.cu
+
+namespace {
+
+constexpr int kFiltThreads = 1024;
+constexpr unsigned long long kInvalidVoxel = 0xffffffffull;   // sorts behind every real voxel index (< 2^31)
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+struct Box {
+  float mn[3], mx[3];
+  int negative;
+};
+__device__ __forceinline__ bool crop_keeps(const Box& b, float x, float y, float z) {
+  if (!finite3(x, y, z)) return false;                                          // crop_box.hpp: non-finite points are skipped
+  const bool outside = (x < b.mn[0] || y < b.mn[1] || z < b.mn[2]) || (x > b.mx[0] || y > b.mx[1] || z > b.mx[2]);
+  return outside ? (b.negative != 0) : (b.negative == 0);
+}
+
+// stable in-block rank of the threads whose flag is set; returns the block total through *total
+__device__ __forceinline__ unsigned int block_rank(bool flag, unsigned int* total) {
+  __shared__ unsigned int wsum[kFiltThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) wsum[warp] = __popc(m);
+  __syncthreads();
+  unsigned int before = 0, all = 0;
+  for (int w = 0; w < kFiltThreads / 32; w++) {
+    const unsigned int c = wsum[w];
+    if (w < warp) before += c;
+    all += c;
+  }
+  __syncthreads();
+  *total = all;
+  return before + __popc(m & ((1u << lane) - 1u));
+}
+
+// pass 1 of a stable compaction: kept points per block
+__global__ void __launch_bounds__(kFiltThreads) crop_count_kernel(const float* __restrict__ xyz, int stride, int n, Box box, unsigned int* __restrict__ block_sums) {
+  const int i = blockIdx.x * kFiltThreads + threadIdx.x;
+  bool keep = false;
+  if (i < n) keep = crop_keeps(box, xyz[(size_t)i * stride], xyz[(size_t)i * stride + 1], xyz[(size_t)i * stride + 2]);
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned int)c;
+}
+
+// exclusive scan of the block sums by one block; the grand total goes to the host-mapped slot
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restrict__ sums, int nblocks, unsigned int* __restrict__ total_dev,
+                                                         ReduceSlot* __restrict__ slot, unsigned long long seq) {
+  __shared__ unsigned int s[1024];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned int v = i < nblocks ? sums[i] : 0u;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const unsigned int t = threadIdx.x >= off ? s[threadIdx.x - off] : 0u;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblocks) sums[i] = carry + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total_dev = carry;
+    slot->v[0] = (double)carry;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&slot->seq) = seq;
+  }
+}
+
+__global__ void __launch_bounds__(kFiltThreads) crop_scatter_kernel(const float* __restrict__ xyz, int stride, int n, Box box,
+                                                                    const unsigned int* __restrict__ block_offs, float4* __restrict__ out) {
+  const int i = blockIdx.x * kFiltThreads + threadIdx.x;
+  bool keep = false;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (i < n) {
+    x = xyz[(size_t)i * stride]; y = xyz[(size_t)i * stride + 1]; z = xyz[(size_t)i * stride + 2];
+    keep = crop_keeps(box, x, y, z);
+  }
+  unsigned int total;
+  const unsigned int r = block_rank(keep, &total);
+  if (keep) out[block_offs[blockIdx.x] + r] = make_float4(x, y, z, 1.0f);
+}
+
+// ---- VoxelGrid ----
+struct VoxelMeta {
+  unsigned int lo[3], hi[3];   // ordered-int min / max of the finite points
+  int min_b[3], div_b[3];
+  int overflow;                // voxel count does not fit int32: PCL returns the input unchanged
+  int pad;
+};
+
+__global__ void __launch_bounds__(256) vg_init_kernel(VoxelMeta* m, uint32_t* digit_hist, int n_hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3) { m->lo[i] = 0xffffffffu; m->hi[i] = 0u; }
+  if (i == 0) m->overflow = 0;
+  if (i < n_hist) digit_hist[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) vg_minmax_kernel(const float* __restrict__ xyz, int stride, int n, VoxelMeta* __restrict__ m) {
+  unsigned int l[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, u[3] = {0u, 0u, 0u};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = xyz[(size_t)i * stride], y = xyz[(size_t)i * stride + 1], z = xyz[(size_t)i * stride + 2];
+    if (!finite3(x, y, z)) continue;                                            // getMinMax3D on a non-dense cloud
+    const unsigned int o[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+    for (int a = 0; a < 3; a++) { l[a] = min(l[a], o[a]); u[a] = max(u[a], o[a]); }
+  }
+  __shared__ unsigned int sl[8][3], su[8][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      l[a] = min(l[a], __shfl_xor_sync(0xffffffffu, l[a], off));
+      u[a] = max(u[a], __shfl_xor_sync(0xffffffffu, u[a], off));
+    }
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5][a] = l[a]; su[threadIdx.x >> 5][a] = u[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned int ml = sl[0][threadIdx.x], mu = su[0][threadIdx.x];
+    for (int w = 1; w < 8; w++) { ml = min(ml, sl[w][threadIdx.x]); mu = max(mu, su[w][threadIdx.x]); }
+    atomicMin(&m->lo[threadIdx.x], ml);
+    atomicMax(&m->hi[threadIdx.x], mu);
+  }
+}
+
+// voxel index of every point (voxel_grid.hpp: "First pass: go over all points and insert them into the index_vector")
+// + the radix sort's digit totals
+__global__ void __launch_bounds__(256) vg_keys_kernel(const float* __restrict__ xyz, int stride, int n, float3 inv_leaf, VoxelMeta* __restrict__ m,
+                                                      unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ digit_hist) {
+  __shared__ uint32_t hsm[4 * kSortRadix];
+  for (int t = threadIdx.x; t < 4 * kSortRadix; t += blockDim.x) hsm[t] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float il[3] = {inv_leaf.x, inv_leaf.y, inv_leaf.z};
+  int min_b[3], div_b[3];
+  long long cells = 1;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float mn = ord2f(m->lo[a]), mx = ord2f(m->hi[a]);
+    min_b[a] = (int)floorf(__fmul_rn(mn, il[a]));
+    const int max_b = (int)floorf(__fmul_rn(mx, il[a]));
+    div_b[a] = max_b - min_b[a] + 1;
+    cells *= (long long)(__fmul_rn(__fsub_rn(mx, mn), il[a])) + 1;             // the int64 dx*dy*dz overflow test of PCL
+  }
+  if (i == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { m->min_b[a] = min_b[a]; m->div_b[a] = div_b[a]; }
+    m->overflow = cells > 2147483647ll ? 1 : 0;
+  }
+  if (i < n) {
+    const float p[3] = {xyz[(size_t)i * stride], xyz[(size_t)i * stride + 1], xyz[(size_t)i * stride + 2]};
+    unsigned long long key = kInvalidVoxel;
+    if (finite3(p[0], p[1], p[2])) {
+      int ijk[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) ijk[a] = (int)__fsub_rn(floorf(__fmul_rn(p[a], il[a])), (float)min_b[a]);
+      key = (unsigned long long)(unsigned int)(ijk[0] + ijk[1] * div_b[0] + ijk[2] * div_b[0] * div_b[1]);
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+#pragma unroll
+    for (int ps = 0; ps < 4; ps++) atomicAdd(&hsm[ps * kSortRadix + sort_digit_of(key, 0, ps)], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 4 * kSortRadix; t += blockDim.x)
+    if (hsm[t]) atomicAdd(&digit_hist[t], hsm[t]);
+}
+
+__device__ __forceinline__ bool voxel_head(const unsigned long long* __restrict__ keys, int j, int n) {
+  if (j >= n) return false;
+  const unsigned long long k = keys[j];
+  return k != kInvalidVoxel && (j == 0 || keys[j - 1] != k);
+}
+
+__global__ void __launch_bounds__(kFiltThreads) vg_count_kernel(const unsigned long long* __restrict__ keys, int n, unsigned int* __restrict__ block_sums) {
+  const int j = blockIdx.x * kFiltThreads + threadIdx.x;
+  const int c = __syncthreads_count(voxel_head(keys, j, n));
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned int)c;
+}
+
+// one thread per occupied voxel (the first point of its run in the sorted order): fp32 sum of its points in ascending
+// input order, divided by the count (pcl::CentroidPoint / AccumulatorXYZ); .w carries the count
+__global__ void __launch_bounds__(kFiltThreads) vg_centroid_kernel(const float* __restrict__ xyz, int stride, int n, const unsigned long long* __restrict__ keys,
+                                                                   const uint32_t* __restrict__ vals, const unsigned int* __restrict__ block_offs,
+                                                                   float4* __restrict__ out, int* __restrict__ out_voxel) {
+  const int j = blockIdx.x * kFiltThreads + threadIdx.x;
+  const bool head = voxel_head(keys, j, n);
+  unsigned int total;
+  const unsigned int r = block_rank(head, &total);
+  if (!head) return;
+  const unsigned long long k = keys[j];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int cnt = 0;
+  for (int t = j; t < n && keys[t] == k; t++) {
+    const float* p = xyz + (size_t)vals[t] * stride;
+    sx = __fadd_rn(sx, p[0]); sy = __fadd_rn(sy, p[1]); sz = __fadd_rn(sz, p[2]);
+    cnt++;
+  }
+  const float fc = (float)cnt;
+  const unsigned int pos = block_offs[blockIdx.x] + r;
+  out[pos] = make_float4(__fdiv_rn(sx, fc), __fdiv_rn(sy, fc), __fdiv_rn(sz, fc), fc);
+  if (out_voxel) out_voxel[pos] = (int)k;
+}
+
+__global__ void __launch_bounds__(256) f4_to_xyz_kernel(const float4* __restrict__ in, int n, float* __restrict__ out3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float4 p = in[i]; out3[3 * (size_t)i] = p.x; out3[3 * (size_t)i + 1] = p.y; out3[3 * (size_t)i + 2] = p.z; }
+}
+__global__ void __launch_bounds__(256) strided_to_f4_kernel(const float* __restrict__ in, int stride, int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(in[(size_t)i * stride], in[(size_t)i * stride + 1], in[(size_t)i * stride + 2], 1.0f);
+}
+
+int wait_count(Handle* h, unsigned long long seq, size_t* out) {
+  volatile unsigned long long* p = &h->slot_host[0].seq;
+  unsigned long long spins = 0;
+  while (*p != seq) {
+    if ((++spins & 0x3fff) != 0) continue;
+    const cudaError_t q = cudaStreamQuery(h->stream);
+    if (q == cudaErrorNotReady) continue;
+    if (q != cudaSuccess) return fail(h, NGICP_ERR_CUDA, std::string("filter kernel: ") + cudaGetErrorString(q));
+    if (*p != seq) return fail(h, NGICP_ERR_CUDA, "filter kernel finished without writing its count");
+  }
+  __sync_synchronize();
+  *out = (size_t)(h->slot_host[0].v[0] + 0.5);
+  return NGICP_OK;
+}
+
+}  // namespace
+
+// d_in: n points, `stride` floats apart, on the device. *d_out: new float4 array (caller frees), *n_out its length.
+int crop_box_device(Handle* h, const float* d_in, int stride, int n, const float mn[3], const float mx[3], int negative, float4** d_out, size_t* n_out) {
+  cudaStream_t s = h->stream;
+  Box box;
+  for (int a = 0; a < 3; a++) { box.mn[a] = mn[a]; box.mx[a] = mx[a]; }
+  box.negative = negative;
+  const int nb = (n + kFiltThreads - 1) / kFiltThreads;
+  unsigned int* d_sums = nullptr;
+  NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 1, s));
+  NGICP_CUDA(h, dev_alloc(d_out, (size_t)n, s));
+  const unsigned long long seq = ++h->seq;
+  crop_count_kernel<<<nb, kFiltThreads, 0, s>>>(d_in, stride, n, box, d_sums);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
+  crop_scatter_kernel<<<nb, kFiltThreads, 0, s>>>(d_in, stride, n, box, d_sums, *d_out);
+  count_launch(h, 3);
+  NGICP_CUDA(h, cudaGetLastError());
+  const int rc = wait_count(h, seq, n_out);
+  dev_free(d_sums, s);
+  return rc;
+}
+
+// *d_out: new float4 array of the voxel centroids (w = points in the voxel), ascending voxel index.
+int voxel_grid_device(Handle* h, const float* d_in, int stride, int n, const float leaf[3], float4** d_out, size_t* n_out, int* d_out_voxel) {
+  cudaStream_t s = h->stream;
+  for (int a = 0; a < 3; a++)
+    if (!(leaf[a] > 0.f)) return fail(h, NGICP_ERR_INVALID, "voxel grid: leaf size must be positive");
+  const float3 inv_leaf = make_float3(1.0f / leaf[0], 1.0f / leaf[1], 1.0f / leaf[2]);   // Array4f::Ones() / leaf_size_
+  const int nbits = 32, passes = sort_num_passes(nbits);
+  auto align_up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_keys_a = 0, o_keys_b = o_keys_a + align_up(sizeof(unsigned long long) * (size_t)n), o_vals_a = o_keys_b + align_up(sizeof(unsigned long long) * (size_t)n),
+               o_vals_b = o_vals_a + align_up(sizeof(uint32_t) * (size_t)n), o_sort = o_vals_b + align_up(sizeof(uint32_t) * (size_t)n),
+               o_meta = o_sort + align_up(sizeof(uint32_t) * sort_scratch_elems(n, nbits)), bytes = o_meta + align_up(sizeof(VoxelMeta));
+  char* scratch = nullptr;
+  NGICP_CUDA(h, dev_alloc(&scratch, bytes, s));
+  unsigned long long* keys_a = reinterpret_cast<unsigned long long*>(scratch + o_keys_a);
+  unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(scratch + o_keys_b);
+  uint32_t* vals_a = reinterpret_cast<uint32_t*>(scratch + o_vals_a);
+  uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + o_vals_b);
+  uint32_t* sort_scratch = reinterpret_cast<uint32_t*>(scratch + o_sort);
+  VoxelMeta* meta = reinterpret_cast<VoxelMeta*>(scratch + o_meta);
+  const int nb256 = (n + 255) / 256;
+  vg_init_kernel<<<(passes * kSortRadix + 255) / 256, 256, 0, s>>>(meta, sort_scratch, passes * kSortRadix);
+  vg_minmax_kernel<<<std::min(nb256, 148), 256, 0, s>>>(d_in, stride, n, meta);
+  vg_keys_kernel<<<nb256, 256, 0, s>>>(d_in, stride, n, inv_leaf, meta, keys_a, vals_a, sort_scratch);
+  count_launch(h, 3);
+  unsigned long long* keys_sorted = nullptr;
+  uint32_t* vals_sorted = nullptr;
+  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  const int nb = (n + kFiltThreads - 1) / kFiltThreads;
+  unsigned int* d_sums = nullptr;
+  NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 1, s));
+  NGICP_CUDA(h, dev_alloc(d_out, (size_t)n, s));
+  const unsigned long long seq = ++h->seq;
+  vg_count_kernel<<<nb, kFiltThreads, 0, s>>>(keys_sorted, n, d_sums);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
+  vg_centroid_kernel<<<nb, kFiltThreads, 0, s>>>(d_in, stride, n, keys_sorted, vals_sorted, d_sums, *d_out, d_out_voxel);
+  count_launch(h, 3);
+  NGICP_CUDA(h, cudaGetLastError());
+  int rc = wait_count(h, seq, n_out);
+  int overflow = 0;
+  if (!rc) {
+    NGICP_CUDA(h, cudaMemcpyAsync(&overflow, &meta->overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NGICP_CUDA(h, cudaStreamSynchronize(s));
+  }
+  dev_free(d_sums, s);
+  dev_free(scratch, s);
+  if (!rc && overflow) {
+    // "Leaf size is too small for the input dataset. Integer indices would overflow." -> output = input (voxel_grid.hpp)
+    strided_to_f4_kernel<<<nb256, 256, 0, s>>>(d_in, stride, n, *d_out);
+    count_launch(h);
+    *n_out = (size_t)n;
+  }
+  return rc;
+}
+
+}  // namespace ngicp
+
+using namespace ngicp;
+
+extern "C" {
+
+int ngicp_filter_scan(ngicp_handle* p, const void* points, size_t n, size_t stride_bytes, const float crop_min[3], const float crop_max[3],
+                      int crop_negative, const float leaf[3], int set_as, float* out_xyz, size_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(p);
+  if (!h || !points || n == 0 || !n_out) return fail(h, NGICP_ERR_INVALID, "ngicp_filter_scan: bad argument");
+  if (set_as < -1 || set_as > 1) return fail(h, NGICP_ERR_INVALID, "ngicp_filter_scan: set_as must be -1, 0 (source) or 1 (target)");
+  if ((crop_min == nullptr) != (crop_max == nullptr)) return fail(h, NGICP_ERR_INVALID, "ngicp_filter_scan: crop_min and crop_max go together");
+  if (n >= (size_t)1 << 31) return fail(h, NGICP_ERR_UNSUPPORTED, "ngicp_filter_scan: more than 2^31 points");
+  if (int rc = select_device(h)) return rc;
+  cudaStream_t s = h->stream;
+  float* d_in = nullptr;
+  int stride = 3;
+  if (int rc = upload_points(h, points, n, stride_bytes, &d_in, &stride)) return rc;
+  const float* cur = d_in;
+  size_t cur_n = n;
+  float4* d_crop = nullptr;
+  float4* d_vox = nullptr;
+  int rc = NGICP_OK;
+  if (crop_min) {
+    rc = crop_box_device(h, cur, stride, (int)cur_n, crop_min, crop_max, crop_negative, &d_crop, &cur_n);
+    if (!rc) { cur = reinterpret_cast<const float*>(d_crop); stride = 4; }
+  }
+  if (!rc && leaf && cur_n > 0) {
+    rc = voxel_grid_device(h, cur, stride, (int)cur_n, leaf, &d_vox, &cur_n, nullptr);
+    if (!rc) { cur = reinterpret_cast<const float*>(d_vox); stride = 4; }
+  }
+  if (!rc && out_xyz && cur_n > 0) {
+    float* d_o = nullptr;
+    NGICP_CUDA(h, dev_alloc(&d_o, cur_n * 3, s));
+    if (stride == 4) {
+      f4_to_xyz_kernel<<<((int)cur_n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4*>(cur), (int)cur_n, d_o);
+      count_launch(h);
+      NGICP_CUDA(h, cudaMemcpyAsync(out_xyz, d_o, cur_n * 12, cudaMemcpyDeviceToHost, s));
+    } else {
+      NGICP_CUDA(h, cudaMemcpy2DAsync(out_xyz, 12, cur, (size_t)stride * 4, 12, cur_n, cudaMemcpyDeviceToHost, s));
+    }
+    NGICP_CUDA(h, cudaStreamSynchronize(s));
+    dev_free(d_o, s);
+  }
+  if (!rc && set_as >= 0) {
+    if (cur_n == 0) rc = fail(h, NGICP_ERR_INVALID, "ngicp_filter_scan: the filters removed every point");
+    else {
+      Index* idx = nullptr;
+      rc = build_index(h, cur, stride, (int)cur_n, nullptr, 1, &idx);
+      if (!rc) rc = swap_in_index(h, set_as, idx);
+    }
+  }
+  *n_out = cur_n;
+  dev_free(d_in, s); dev_free(d_crop, s); dev_free(d_vox, s);
+  return rc;
+}
+
+}  // extern "C"

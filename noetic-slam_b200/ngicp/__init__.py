@@ -5,7 +5,7 @@ The repo directory is `noetic-slam_b200/` (not an importable name), so callers p
 """
 from .binding import (NgicpError, REG_FROBENIUS, REG_MIN_EIG, REG_NONE, REG_NORMALIZED_MIN_EIG, REG_PLANE, SOURCE, TARGET,
                       LIB_PATH, build, lib)
-from .gicp import KdTreeFLANN, NanoGICP
+from .gicp import CropBox, KdTreeFLANN, NanoGICP, VoxelGrid
 
-__all__ = ["NanoGICP", "KdTreeFLANN", "NgicpError", "build", "lib", "LIB_PATH", "REG_NONE", "REG_MIN_EIG",
+__all__ = ["NanoGICP", "KdTreeFLANN", "CropBox", "VoxelGrid", "NgicpError", "build", "lib", "LIB_PATH", "REG_NONE", "REG_MIN_EIG",
            "REG_NORMALIZED_MIN_EIG", "REG_PLANE", "REG_FROBENIUS", "SOURCE", "TARGET"]

@@ -186,6 +186,15 @@ class NanoGICP:
         self.source_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.SOURCE), token)
         self._input = token
 
+    def setInputSourceFiltered(self, cloud, crop=None, leaf=None):
+        """CropBox -> VoxelGrid -> setInputSource without leaving the device (DLIO's getScanFromROS / preprocessPoints
+        order, odom.cc:500-502 and :575-584). crop = (min_xyz, max_xyz, negative) or None; leaf = (lx, ly, lz) or None.
+        Returns the filtered cloud (host copy, the cloud DLIO would have handed to setInputSource)."""
+        out = _filter_scan(self, cloud, crop, leaf, B.SOURCE)
+        self.source_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.SOURCE), out)
+        self._input = out
+        return out
+
     def registerInputSource(self, cloud):  # nano_gicp.cc:119-124: stores the cloud only
         self._input = cloud
 
@@ -369,3 +378,52 @@ class NanoGICP:
 
     def synchronize(self):
         B.check(self._h, self._L.ngicp_synchronize(self._h))
+
+
+# ---- scan pre-filters on the device: PCL's class names as DLIO uses them (odom.cc:114-118, :500-502, :575-584) -------------
+def _filter_scan(owner: "NanoGICP", cloud, crop, leaf, set_as: int):
+    p = _pts(cloud)
+    fp = C.POINTER(C.c_float)
+    if crop is not None:
+        mn = np.ascontiguousarray(crop[0], np.float32); mx = np.ascontiguousarray(crop[1], np.float32)
+        a_mn, a_mx, neg = mn.ctypes.data_as(fp), mx.ctypes.data_as(fp), int(bool(crop[2]))
+    else:
+        a_mn = a_mx = None; neg = 0
+    lf = None if leaf is None else np.ascontiguousarray(leaf, np.float32)
+    out = np.empty((p.shape[0], 3), np.float32)
+    n_out = C.c_size_t(0)
+    B.check(owner._h, owner._L.ngicp_filter_scan(owner._h, p.ctypes.data, p.shape[0], p.strides[0], a_mn, a_mx, neg,
+                                                 None if lf is None else lf.ctypes.data_as(fp), set_as, out.ctypes.data_as(fp), C.byref(n_out)))
+    return out[:n_out.value].copy()
+
+
+class CropBox:
+    """pcl::CropBox on the device (ngicp_filter_scan): setMin / setMax / setNegative / setInputCloud / filter."""
+
+    def __init__(self, owner: "NanoGICP"):
+        self._o = owner
+        self._min = np.full(3, -1.0, np.float32); self._max = np.full(3, 1.0, np.float32); self._neg = False; self._cloud = None
+
+    def setMin(self, v): self._min = np.asarray(v, np.float32)[:3].copy()
+    def setMax(self, v): self._max = np.asarray(v, np.float32)[:3].copy()
+    def setNegative(self, b): self._neg = bool(b)
+    def setInputCloud(self, cloud): self._cloud = cloud
+
+    def filter(self):
+        return _filter_scan(self._o, self._cloud, (self._min, self._max, self._neg), None, -1)
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid on the device (ngicp_filter_scan): setLeafSize / setInputCloud / filter."""
+
+    def __init__(self, owner: "NanoGICP"):
+        self._o = owner
+        self._leaf = np.full(3, 0.05, np.float32); self._cloud = None
+
+    def setLeafSize(self, lx, ly=None, lz=None):
+        self._leaf = np.array([lx, lx if ly is None else ly, lx if lz is None else lz], np.float32)
+
+    def setInputCloud(self, cloud): self._cloud = cloud
+
+    def filter(self):
+        return _filter_scan(self._o, self._cloud, None, self._leaf, -1)

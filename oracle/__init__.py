@@ -79,6 +79,10 @@ def lib(variant: str = "port") -> C.CDLL:
     L.orc_gicp_get_covs.argtypes = [vp, i, dp]
     L.orc_gicp_set_covs.argtypes = [vp, i, dp, sz]
     L.orc_gicp_update_correspondences.argtypes = [vp, dp, ip, fp, dp]
+    L.orc_crop_box.restype = sz
+    L.orc_crop_box.argtypes = [fp, sz, sz, fp, fp, i, fp]
+    L.orc_voxel_grid.restype = sz
+    L.orc_voxel_grid.argtypes = [fp, sz, sz, fp, fp, ip, ip]
     L.orc_gicp_num_correspondences.restype = i
     L.orc_gicp_num_correspondences.argtypes = [vp]
     L.orc_gicp_linearize.restype = d
@@ -236,3 +240,56 @@ class OracleGICP:
     def getFinalTransformation(self): return self.final_transformation_
     def getFinalHessian(self): return self.final_hessian_
     def getFinalError(self): return self.final_error_
+
+
+# ---- scan pre-filters: PCL's names (pcl::CropBox / pcl::VoxelGrid as DLIO configures them, odom.cc:114-118) --------------
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError(f"cloud must be (N, >=3) float32, got {a.shape}")
+    return a
+
+
+class CropBox:
+    """pcl::CropBox restated (oracle.cc:orc_crop_box): setMin / setMax / setNegative / setInputCloud / filter."""
+
+    def __init__(self, variant: str = "port"):
+        self._L = lib(variant)
+        self._min = np.full(3, -1.0, np.float32); self._max = np.full(3, 1.0, np.float32); self._neg = False; self._cloud = None
+
+    def setMin(self, v): self._min = np.asarray(v, np.float32)[:3].copy()
+    def setMax(self, v): self._max = np.asarray(v, np.float32)[:3].copy()
+    def setNegative(self, b): self._neg = bool(b)
+    def setInputCloud(self, cloud): self._cloud = _f32(cloud)
+
+    def filter(self):
+        c = self._cloud
+        out = np.empty((len(c), 3), np.float32)
+        fp = C.POINTER(C.c_float)
+        m = self._L.orc_crop_box(c.ctypes.data_as(fp), len(c), c.strides[0] // 4, self._min.ctypes.data_as(fp), self._max.ctypes.data_as(fp),
+                                 int(self._neg), out.ctypes.data_as(fp))
+        return out[:m].copy()
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid restated (oracle.cc:orc_voxel_grid): setLeafSize / setInputCloud / filter."""
+
+    def __init__(self, variant: str = "port"):
+        self._L = lib(variant)
+        self._leaf = np.full(3, 0.05, np.float32); self._cloud = None
+        self.voxel_index = None; self.voxel_count = None
+
+    def setLeafSize(self, lx, ly=None, lz=None):
+        self._leaf = np.array([lx, lx if ly is None else ly, lx if lz is None else lz], np.float32)
+
+    def setInputCloud(self, cloud): self._cloud = _f32(cloud)
+
+    def filter(self):
+        c = self._cloud
+        out = np.empty((len(c), 3), np.float32)
+        vox = np.empty(len(c), np.int32); cnt = np.empty(len(c), np.int32)
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        m = self._L.orc_voxel_grid(c.ctypes.data_as(fp), len(c), c.strides[0] // 4, self._leaf.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                                   vox.ctypes.data_as(ip), cnt.ctypes.data_as(ip))
+        self.voxel_index, self.voxel_count = vox[:m].copy(), cnt[:m].copy()
+        return out[:m].copy()

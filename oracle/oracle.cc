@@ -36,6 +36,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <memory>
 #include <numeric>
 #include <vector>
@@ -700,6 +701,76 @@ int orc_gicp_align(Gicp* g, const float guess[16], float T_out[16], int* nr_iter
   if (H_final) std::memcpy(H_final, g->final_hessian, sizeof g->final_hessian);
   if (final_err) *final_err = g->final_error;
   return rc;
+}
+
+// ---- scan pre-filters ------------------------------------------------------------------------
+// PCL (>= 1.10.0, apt libpcl-dev; src/dlio/README.md:31) is a third-party dependency that is NOT part of the reference
+// tree, so these two functions restate PCL 1.10's published algorithms as DLIO calls them (xyz only):
+//   pcl::CropBox<PointT>::applyFilter   (filters/impl/crop_box.hpp)    reference call sites odom.cc:114-116, :500-502
+//   pcl::VoxelGrid<PointT>::applyFilter (filters/impl/voxel_grid.hpp)  reference call sites odom.cc:118, :575-584
+// Parity with a real PCL is unpinned (no PCL in this image, no fixtures in the reference). One deliberate pin: PCL sorts
+// the (voxel index, point index) pairs with std::sort, whose order inside a voxel is unspecified, so PCL's own fp32
+// centroid sums are defined only up to rounding; here the order is ascending point index (std::stable_sort).
+
+// keeps a finite point iff (inside the box) != negative; returns the number kept; out = n x 3 floats capacity
+size_t orc_crop_box(const float* pts, size_t n, size_t stride_floats, const float mn[3], const float mx[3], int negative, float* out) {
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) {
+    const float* p = pts + i * stride_floats;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;   // crop_box.hpp: "Check if the point is invalid"
+    const bool outside = (p[0] < mn[0] || p[1] < mn[1] || p[2] < mn[2]) || (p[0] > mx[0] || p[1] > mx[1] || p[2] > mx[2]);
+    if (outside ? (negative != 0) : (negative == 0)) {
+      out[3 * m] = p[0]; out[3 * m + 1] = p[1]; out[3 * m + 2] = p[2];
+      m++;
+    }
+  }
+  return m;
+}
+
+// out = n x 3 floats capacity, out_voxel / out_count (optional) = voxel index and population of every output point
+size_t orc_voxel_grid(const float* pts, size_t n, size_t stride_floats, const float leaf[3], float* out, int* out_voxel, int* out_count) {
+  float inv[3], mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int a = 0; a < 3; a++) inv[a] = 1.0f / leaf[a];                                     // Array4f::Ones() / leaf_size_
+  for (size_t i = 0; i < n; i++) {                                                          // getMinMax3D, non-dense cloud
+    const float* p = pts + i * stride_floats;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+  }
+  long long cells = 1;
+  int min_b[3], div_b[3];
+  for (int a = 0; a < 3; a++) {
+    cells *= static_cast<long long>((mx[a] - mn[a]) * inv[a]) + 1;
+    min_b[a] = static_cast<int>(std::floor(mn[a] * inv[a]));
+    div_b[a] = static_cast<int>(std::floor(mx[a] * inv[a])) - min_b[a] + 1;
+  }
+  if (cells > static_cast<long long>(INT32_MAX)) {                                          // "Leaf size is too small": output = input
+    for (size_t i = 0; i < n; i++) for (int a = 0; a < 3; a++) out[3 * i + a] = pts[i * stride_floats + a];
+    return n;
+  }
+  std::vector<std::pair<unsigned int, unsigned int>> iv;                                    // (voxel idx, point index)
+  iv.reserve(n);
+  for (size_t i = 0; i < n; i++) {
+    const float* p = pts + i * stride_floats;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    int ijk[3];
+    for (int a = 0; a < 3; a++) ijk[a] = static_cast<int>(std::floor(p[a] * inv[a]) - static_cast<float>(min_b[a]));
+    iv.emplace_back(static_cast<unsigned int>(ijk[0] + ijk[1] * div_b[0] + ijk[2] * div_b[0] * div_b[1]), static_cast<unsigned int>(i));
+  }
+  std::stable_sort(iv.begin(), iv.end(), [](const std::pair<unsigned int, unsigned int>& a, const std::pair<unsigned int, unsigned int>& b) { return a.first < b.first; });
+  size_t m = 0;
+  for (size_t j = 0; j < iv.size();) {
+    float s[3] = {0.f, 0.f, 0.f};                                                           // AccumulatorXYZ: Eigen::Vector3f xyz
+    size_t e = j;
+    for (; e < iv.size() && iv[e].first == iv[j].first; e++)
+      for (int a = 0; a < 3; a++) s[a] += pts[iv[e].second * stride_floats + a];
+    const float cnt = static_cast<float>(e - j);
+    for (int a = 0; a < 3; a++) out[3 * m + a] = s[a] / cnt;
+    if (out_voxel) out_voxel[m] = static_cast<int>(iv[j].first);
+    if (out_count) out_count[m] = static_cast<int>(e - j);
+    m++;
+    j = e;
+  }
+  return m;
 }
 
 }  // extern "C"

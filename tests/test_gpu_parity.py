@@ -474,3 +474,70 @@ def test_device_keyframe_store_matches_host_round_trip():
     o.setInputSource(src); o.calculateSourceCovariances()
     To = o.align()
     assert np.abs(T_dev[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(T_dev[:3, :3], To[:3, :3]) < POSE_R_TOL
+
+
+# ----------------------------------------------------------------------------------- f-2: scan pre-filters
+def _scan_with_nans(seed=0):
+    a, _, _ = S.scan_pair(seed, w=256)
+    a = a.copy()
+    a[::97, 1] = np.nan                      # removeNaNFromPointCloud territory (odom.cc:496-498)
+    a[5::211, 2] = np.inf
+    return a
+
+
+@pytest.mark.parametrize("negative", [True, False])
+def test_crop_box_matches_the_pcl_restatement(gicp, negative):
+    a = _scan_with_nans(0)
+    for size in (1.0, 3.5):
+        c = ngicp.CropBox(gicp); o = oracle.CropBox()
+        for f in (c, o):
+            f.setNegative(negative); f.setMin([-size] * 3); f.setMax([size] * 3); f.setInputCloud(a)
+        out, ref = c.filter(), o.filter()
+        assert out.shape == ref.shape and (out == ref).all()     # same points, same order, bit for bit
+    assert np.isfinite(out).all()
+
+
+@pytest.mark.parametrize("leaf", [0.1, 0.25, (0.5, 0.2, 0.3)])
+def test_voxel_grid_matches_the_pcl_restatement(gicp, leaf):
+    a = _scan_with_nans(1)
+    v = ngicp.VoxelGrid(gicp); o = oracle.VoxelGrid()
+    for f in (v, o):
+        f.setLeafSize(*((leaf,) if np.isscalar(leaf) else leaf)); f.setInputCloud(a)
+    out, ref = v.filter(), o.filter()
+    assert out.shape == ref.shape                                # one point per occupied voxel, ascending voxel index
+    assert (out == ref).all()                                    # fp32 sums in ascending input order: bit-exact
+    assert (np.diff(o.voxel_index) > 0).all() and o.voxel_count.sum() == np.isfinite(a).all(1).sum()
+
+
+def test_voxel_grid_edge_cases(gicp):
+    v = ngicp.VoxelGrid(gicp); o = oracle.VoxelGrid()
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    same = np.repeat(one, 500, 0)
+    rng = np.random.default_rng(3)
+    huge = np.concatenate([rng.uniform(-1, 1, (1000, 3)), [[5e4, 5e4, 5e4]]]).astype(np.float32)   # 1e5/0.01 cells per axis: int32 overflow
+    for cloud, leaf in ((one, 0.25), (same, 0.25), (huge, 0.01), (huge, 10.0)):
+        for f in (v, o):
+            f.setLeafSize(leaf); f.setInputCloud(cloud)
+        out, ref = v.filter(), o.filter()
+        assert out.shape == ref.shape and (out == ref).all()
+    with pytest.raises(ngicp.NgicpError):
+        v.setLeafSize(0.0); v.setInputCloud(one); v.filter()
+
+
+def test_filtered_scan_becomes_the_source_without_leaving_the_device():
+    """setInputSourceFiltered == CropBox -> VoxelGrid -> setInputSource of DLIO (odom.cc:500-502, :575-584, :1001):
+    the registration that follows is identical to feeding the oracle the PCL-filtered cloud."""
+    a, b, _ = S.scan_pair(4, w=256)
+    g = S.configure(ngicp.NanoGICP(0)); o = S.configure(oracle.OracleGICP("port"))
+    crop = ([-1.0] * 3, [1.0] * 3, True)
+    filt = g.setInputSourceFiltered(a, crop=crop, leaf=(0.25, 0.25, 0.25))
+    oc = oracle.CropBox(); oc.setNegative(True); oc.setMin(crop[0]); oc.setMax(crop[1]); oc.setInputCloud(a)
+    ov = oracle.VoxelGrid(); ov.setLeafSize(0.25); ov.setInputCloud(oc.filter())
+    ref = ov.filter()
+    assert filt.shape == ref.shape and (filt == ref).all()
+    o.setInputSource(ref)
+    for x in (g, o):
+        x.setInputTarget(b); x.calculateSourceCovariances(); x.calculateTargetCovariances()
+    Tg, To = g.align(), o.align()
+    assert g.nr_iterations_ == o.nr_iterations_ and g.hasConverged() == o.hasConverged()
+    assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(Tg[:3, :3], To[:3, :3]) < POSE_R_TOL
