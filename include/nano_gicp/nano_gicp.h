@@ -88,6 +88,31 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     target_covs_.reset();
     device_covs_[NGICP_TARGET] = false;
   }
+  // Additive: pcl::CropBox -> pcl::VoxelGrid -> setInputSource in one call that keeps the scan in
+  // HBM (replaces odom.cc:501-502, :579-580 and :721). crop_size <= 0: no crop (DLIO's crop is negative: it removes the
+  // box around the sensor); leaf <= 0: no voxel grid. The filtered cloud (xyz filled in, other fields default) becomes
+  // input_ and is returned, so the caller can still publish it.
+  PointCloudSourceConstPtr setInputSourceFiltered(const PointCloudSourceConstPtr& raw, float crop_size, float leaf) {
+    const float mn[3] = {-crop_size, -crop_size, -crop_size}, mx[3] = {crop_size, crop_size, crop_size}, lf[3] = {leaf, leaf, leaf};
+    std::vector<float> xyz(raw->points.size() * 3);
+    size_t n_out = 0;
+    check(ngicp_filter_scan(h_, raw->points.data(), raw->points.size(), sizeof(PointSource), crop_size > 0 ? mn : nullptr,
+                            crop_size > 0 ? mx : nullptr, 1, leaf > 0 ? lf : nullptr, NGICP_SOURCE, xyz.data(), &n_out));
+    auto cloud = std::make_shared<pcl::PointCloud<PointSource>>();
+    cloud->points.resize(n_out);
+    for (size_t i = 0; i < n_out; i++) { cloud->points[i].x = xyz[3 * i]; cloud->points[i].y = xyz[3 * i + 1]; cloud->points[i].z = xyz[3 * i + 2]; }
+    cloud->width = static_cast<std::uint32_t>(n_out); cloud->height = 1; cloud->is_dense = true;
+    pcl::Registration<PointSource, PointTarget, Scalar>::setInputSource(cloud);
+    auto tree = std::make_shared<nanoflann::KdTreeFLANN<PointSource>>();
+    tree->adopt(cloud, ngicp_get_index(h_, NGICP_SOURCE));
+    attached_[NGICP_SOURCE] = tree->index();
+    uploaded_covs_[NGICP_SOURCE] = nullptr;
+    source_kdtree_ = tree;
+    source_covs_.reset();
+    device_covs_[NGICP_SOURCE] = false;
+    return cloud;
+  }
+  ngicp_handle* handle() const { return h_; }
   virtual void setSourceCovariances(const std::shared_ptr<const CovarianceList>& covs) { source_covs_ = covs; device_covs_[0] = false; }  // :164-166
   virtual void setTargetCovariances(const std::shared_ptr<const CovarianceList>& covs) { target_covs_ = covs; device_covs_[1] = false; }  // :169-171
   virtual void registerInputSource(const PointCloudSourceConstPtr& cloud) {   // nano_gicp.cc:119-124

@@ -55,5 +55,13 @@ int main(int argc, char** argv) {
   std::vector<int> ki; std::vector<float> kd;
   const int found = gicp.target_kdtree_->nearestKSearch(src->points[0], 3, ki, kd);
   std::printf("knn %d %d %d %d %.9g %.9g %.9g\n", found, ki[0], ki[1], ki[2], kd[0], kd[1], kd[2]);
+  // crop + voxel grid + setInputSource in one device call (replaces odom.cc:501-502, :579-580, :721), then align again
+  auto filtered = gicp.setInputSourceFiltered(src, 1.0f, 0.25f);
+  gicp.calculateSourceCovariances();
+  gicp.align(aligned);
+  const auto T2 = gicp.getFinalTransformation();
+  std::printf("filtered %zu first %.9g %.9g %.9g T", filtered->points.size(), filtered->points[0].x, filtered->points[0].y, filtered->points[0].z);
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) std::printf(" %.9g", T2(r, c));
+  std::printf("\n");
   return 0;
 }

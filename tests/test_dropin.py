@@ -53,3 +53,10 @@ def test_dropin_matches_python_mirror(tmp_path):
     k = lines[1].split()
     idx, sqd = g.target_kdtree_.nearestKSearch(b[:1], 3)
     assert [int(x) for x in k[2:5]] == idx[0].tolist() and int(k[1]) == 3
+    f = lines[2].split()
+    filt = g.setInputSourceFiltered(b, crop=([-1.0] * 3, [1.0] * 3, True), leaf=(0.25, 0.25, 0.25))
+    g.calculateSourceCovariances()
+    T2 = g.align()
+    assert int(f[1]) == len(filt) and (np.array([float(x) for x in f[3:6]], np.float32) == filt[0]).all()
+    T2_cpp = np.array([float(x) for x in f[7:23]]).reshape(4, 4)
+    assert np.abs(T2_cpp - T2).max() < 1e-6
