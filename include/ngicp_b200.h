@@ -188,6 +188,23 @@ int ngicp_submap_assemble(ngicp_handle* h, ngicp_keyframe* const* kfs, int n_kfs
 int ngicp_filter_scan(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes, const float crop_min[3], const float crop_max[3],
                       int crop_negative, const float leaf[3], int set_as, float* out_xyz, size_t* n_out);
 
+/* ---- deskew on the device (reference dlio::OdomNode::deskewPointcloud, odom.cc:588-706) ----------
+ * The reference sorts the scan by per-point time stamp (:634-635), lists the unique stamps (:638-650), integrates the
+ * IMU to one pose per unique stamp on the host (:671-672, stays on the host), and moves every point by the pose of its
+ * stamp (:690-701, pt = (frames[i] * baselink2lidar_T) * pt). Two calls, the scan stays in HBM in between:
+ *   ngicp_scan_ingest  removes non-finite points (:496-498), applies the optional CropBox (:500-502), sorts by time
+ *                      stamp (stable: ties keep input order; std::partial_sort_copy leaves them unspecified) and
+ *                      returns the unique stamps, ascending, as raw field values converted to double (the caller adds
+ *                      its sweep reference time as in :612/:622/:632). time_type 0 = uint32 (Ouster `t`), 1 = float
+ *                      (Velodyne `time`), 2 = double (Hesai `timestamp`), at byte offset time_offset_bytes of a record.
+ *   ngicp_scan_deskew  frames16 = n_unique column-major fp32 4x4 matrices (already multiplied by the extrinsic), or ONE
+ *                      matrix for the no-IMU paths (:659, :681: pcl::transformPointCloud of the whole scan);
+ *                      then the optional VoxelGrid (:575-584) and, with set_as 0/1, setInputSource/Target. Output
+ *                      (optional, capacity n_kept x 3 floats) is in time order (no voxel grid) or voxel order. */
+int ngicp_scan_ingest(ngicp_handle* h, const void* points, size_t n, size_t stride_bytes, size_t time_offset_bytes, int time_type,
+                      const float crop_min[3], const float crop_max[3], int crop_negative, double* unique_stamps, size_t* n_unique, size_t* n_kept);
+int ngicp_scan_deskew(ngicp_handle* h, const float* frames16, size_t n_frames, const float leaf[3], int set_as, float* out_xyz, size_t* n_out);
+
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
 typedef struct ngicp_timings {
   float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */

@@ -260,6 +260,8 @@ int ngicp_destroy(ngicp_handle* p) {
   }
   cudaStreamSynchronize(h->stream);
   if (h->corr) cudaFree(h->corr);
+  if (h->scan_pts) cudaFree(h->scan_pts);
+  if (h->scan_keys) cudaFree(h->scan_keys);
   if (h->heavy) cudaFree(h->heavy);
   if (h->heavy_count) cudaFree(h->heavy_count);
   if (h->partials) cudaFree(h->partials);

@@ -14,6 +14,7 @@
 // Same machinery as K1: fused key + digit-histogram kernel, the hand-written stable LSD radix sort, then one pass over
 // the sorted keys. Everything stays in HBM; only the output count comes back (host-mapped slot).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "internal.h"
@@ -249,6 +250,107 @@ __global__ void __launch_bounds__(256) strided_to_f4_kernel(const float* __restr
   if (i < n) out[i] = make_float4(in[(size_t)i * stride], in[(size_t)i * stride + 1], in[(size_t)i * stride + 2], 1.0f);
 }
 
+// ---- deskew (§8f row 3) ----
+// order-preserving 64-bit integer image of a point's time stamp; cropped / non-finite points get the largest key
+constexpr unsigned long long kDroppedStamp = ~0ull;
+__device__ __forceinline__ unsigned long long stamp_key(const unsigned char* rec, int time_type) {
+  if (time_type == 0) return (unsigned long long)*reinterpret_cast<const unsigned int*>(rec);          // Ouster `t`, uint32 ns
+  if (time_type == 1) return (unsigned long long)f2ord(*reinterpret_cast<const float*>(rec));           // Velodyne `time`, float s
+  const unsigned long long u = *reinterpret_cast<const unsigned long long*>(rec);                       // Hesai `timestamp`, double s
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double stamp_value(unsigned long long key, int time_type) {
+  if (time_type == 0) return (double)(unsigned int)key;
+  if (time_type == 1) {
+    const unsigned int o = (unsigned int)key;
+    const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    float f;
+    memcpy(&f, &u, 4);
+    return (double)f;
+  }
+  const unsigned long long u = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
+  double d;
+  memcpy(&d, &u, 8);
+  return d;
+}
+
+__global__ void __launch_bounds__(256) ingest_keys_kernel(const unsigned char* __restrict__ recs, size_t stride_bytes, size_t time_off, int time_type, int n,
+                                                          Box box, int use_box, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                          uint32_t* __restrict__ digit_hist, int passes) {
+  __shared__ uint32_t hsm[8 * kSortRadix];
+  for (int t = threadIdx.x; t < passes * kSortRadix; t += blockDim.x) hsm[t] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned char* rec = recs + (size_t)i * stride_bytes;
+    const float* p = reinterpret_cast<const float*>(rec);
+    const bool keep = use_box ? crop_keeps(box, p[0], p[1], p[2]) : finite3(p[0], p[1], p[2]);
+    unsigned long long key = keep ? stamp_key(rec + time_off, time_type) : kDroppedStamp;
+    if (keep && key == kDroppedStamp) key = kDroppedStamp - 1;   // a NaN stamp: keep the point, sort it last
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    for (int ps = 0; ps < passes; ps++) atomicAdd(&hsm[ps * kSortRadix + sort_digit_of(key, 0, ps)], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < passes * kSortRadix; t += blockDim.x)
+    if (hsm[t]) atomicAdd(&digit_hist[t], hsm[t]);
+}
+
+__device__ __forceinline__ bool stamp_head(const unsigned long long* __restrict__ keys, int j, int n) {
+  if (j >= n) return false;
+  const unsigned long long k = keys[j];
+  return k != kDroppedStamp && (j == 0 || keys[j - 1] != k);
+}
+// block_sums[b] = unique stamps that start in block b; block_sums[nb + 1 + b] = kept points in block b
+__global__ void __launch_bounds__(kFiltThreads) ingest_count_kernel(const unsigned long long* __restrict__ keys, int n, unsigned int* __restrict__ head_sums,
+                                                                    unsigned int* __restrict__ kept_total) {
+  const int j = blockIdx.x * kFiltThreads + threadIdx.x;
+  const int heads = __syncthreads_count(stamp_head(keys, j, n));
+  const int kept = __syncthreads_count(j < n && keys[j] != kDroppedStamp);
+  if (threadIdx.x == 0) { head_sums[blockIdx.x] = (unsigned int)heads; atomicAdd(kept_total, (unsigned int)kept); }
+}
+// gathers the kept points in time order and writes every unique stamp (ascending)
+__global__ void __launch_bounds__(kFiltThreads) ingest_gather_kernel(const unsigned char* __restrict__ recs, size_t stride_bytes, int n,
+                                                                     const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                     const unsigned int* __restrict__ head_offs, int time_type, float4* __restrict__ pts,
+                                                                     double* __restrict__ unique_stamps) {
+  const int j = blockIdx.x * kFiltThreads + threadIdx.x;
+  const bool head = stamp_head(keys, j, n);
+  unsigned int total;
+  const unsigned int r = block_rank(head, &total);
+  if (j >= n) return;
+  const unsigned long long k = keys[j];
+  if (k == kDroppedStamp) return;                   // dropped points sort last: kept points are exactly positions [0, kept)
+  const float* p = reinterpret_cast<const float*>(recs + (size_t)vals[j] * stride_bytes);
+  pts[j] = make_float4(p[0], p[1], p[2], 1.0f);
+  if (head) unique_stamps[head_offs[blockIdx.x] + r] = stamp_value(k, time_type);
+}
+// pt = T_group * pt (odom.cc:690-701): ((m0 x + m1 y) + m2 z) + m3, fp32, no FMA; group = unique stamps up to this point - 1
+__global__ void __launch_bounds__(kFiltThreads) deskew_apply_kernel(const float4* __restrict__ pts, const unsigned long long* __restrict__ keys, int n,
+                                                                    const unsigned int* __restrict__ head_offs, const float* __restrict__ frames, int n_frames,
+                                                                    float4* __restrict__ out) {
+  const int j = blockIdx.x * kFiltThreads + threadIdx.x;
+  const bool head = stamp_head(keys, j, n);
+  // inclusive count of heads up to this thread
+  __shared__ unsigned int wsum[kFiltThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int m = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) wsum[warp] = __popc(m);
+  __syncthreads();
+  unsigned int before = 0;
+  for (int w = 0; w < warp; w++) before += wsum[w];
+  if (j >= n) return;
+  const int g = (int)(head_offs[blockIdx.x] + before + __popc(m & ((2u << lane) - 1u))) - 1;
+  const float* T = frames + (size_t)min(max(g, 0), n_frames - 1) * 16;   // column-major 4x4
+  const float4 p = pts[j];
+  float q[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    q[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[r], p.x), __fmul_rn(T[4 + r], p.y)), __fmul_rn(T[8 + r], p.z)), T[12 + r]);
+  out[j] = make_float4(q[0], q[1], q[2], 1.0f);
+}
+__global__ void zero_u32_kernel(unsigned int* p) { *p = 0u; }
+
 int wait_count(Handle* h, unsigned long long seq, size_t* out) {
   volatile unsigned long long* p = &h->slot_host[0].seq;
   unsigned long long spins = 0;
@@ -395,6 +497,129 @@ int ngicp_filter_scan(ngicp_handle* p, const void* points, size_t n, size_t stri
   }
   *n_out = cur_n;
   dev_free(d_in, s); dev_free(d_crop, s); dev_free(d_vox, s);
+  return rc;
+}
+
+int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stride_bytes, size_t time_offset_bytes, int time_type,
+                      const float crop_min[3], const float crop_max[3], int crop_negative, double* unique_stamps, size_t* n_unique, size_t* n_kept) {
+  Handle* h = reinterpret_cast<Handle*>(p);
+  if (!h || !points || n == 0 || !n_unique) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_ingest: bad argument");
+  if (time_type < 0 || time_type > 2) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_ingest: time_type must be 0 (uint32), 1 (float) or 2 (double)");
+  const size_t tsize = time_type == 2 ? 8 : 4;
+  if (stride_bytes < 12 || stride_bytes % 4 || time_offset_bytes % tsize || time_offset_bytes + tsize > stride_bytes)
+    return fail(h, NGICP_ERR_INVALID, "ngicp_scan_ingest: bad stride or time-stamp offset");
+  if ((crop_min == nullptr) != (crop_max == nullptr)) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_ingest: crop_min and crop_max go together");
+  if (n >= (size_t)1 << 31) return fail(h, NGICP_ERR_UNSUPPORTED, "ngicp_scan_ingest: more than 2^31 points");
+  if (int rc = select_device(h)) return rc;
+  cudaStream_t s = h->stream;
+  dev_free(h->scan_pts, s); dev_free(h->scan_keys, s);
+  h->scan_pts = nullptr; h->scan_keys = nullptr; h->scan_n = 0; h->scan_groups = 0;
+  Box box;
+  for (int a = 0; a < 3; a++) { box.mn[a] = crop_min ? crop_min[a] : 0.f; box.mx[a] = crop_max ? crop_max[a] : 0.f; }
+  box.negative = crop_negative;
+  const int nbits = time_type == 2 ? 64 : 33;   // bit 32 separates the dropped points (all-ones key) from real 32-bit stamps
+  const int passes = sort_num_passes(nbits);
+  unsigned char* d_recs = nullptr;
+  unsigned long long *keys_a = nullptr, *keys_b = nullptr;
+  uint32_t *vals_a = nullptr, *vals_b = nullptr, *sort_scratch = nullptr;
+  unsigned int* d_sums = nullptr;
+  double* d_unique = nullptr;
+  const int nb = ((int)n + kFiltThreads - 1) / kFiltThreads;
+  NGICP_CUDA(h, dev_alloc(&d_recs, n * stride_bytes, s));
+  NGICP_CUDA(h, dev_alloc(&keys_a, n, s));
+  NGICP_CUDA(h, dev_alloc(&keys_b, n, s));
+  NGICP_CUDA(h, dev_alloc(&vals_a, n, s));
+  NGICP_CUDA(h, dev_alloc(&vals_b, n, s));
+  NGICP_CUDA(h, dev_alloc(&sort_scratch, sort_scratch_elems((int)n, nbits), s));
+  NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 2, s));
+  NGICP_CUDA(h, dev_alloc(&d_unique, n, s));
+  NGICP_CUDA(h, dev_alloc(&h->scan_pts, n, s));
+  NGICP_CUDA(h, cudaMemcpyAsync(d_recs, points, n * stride_bytes, cudaMemcpyHostToDevice, s));
+  NGICP_CUDA(h, cudaMemsetAsync(sort_scratch, 0, sizeof(uint32_t) * passes * kSortRadix, s));
+  ingest_keys_kernel<<<((int)n + 255) / 256, 256, 0, s>>>(d_recs, stride_bytes, time_offset_bytes, time_type, (int)n, box, crop_min ? 1 : 0, keys_a, vals_a,
+                                                         sort_scratch, passes);
+  count_launch(h);
+  unsigned long long* keys_sorted = nullptr;
+  uint32_t* vals_sorted = nullptr;
+  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, (int)n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  const unsigned long long seq = ++h->seq;
+  zero_u32_kernel<<<1, 1, 0, s>>>(d_sums + nb + 1);
+  ingest_count_kernel<<<nb, kFiltThreads, 0, s>>>(keys_sorted, (int)n, d_sums, d_sums + nb + 1);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
+  ingest_gather_kernel<<<nb, kFiltThreads, 0, s>>>(d_recs, stride_bytes, (int)n, keys_sorted, vals_sorted, d_sums, time_type, h->scan_pts, d_unique);
+  count_launch(h, 4);
+  NGICP_CUDA(h, cudaGetLastError());
+  size_t groups = 0;
+  int rc = wait_count(h, seq, &groups);
+  unsigned int kept = 0;
+  if (!rc) {
+    NGICP_CUDA(h, cudaMemcpyAsync(&kept, d_sums + nb + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    if (unique_stamps && groups) NGICP_CUDA(h, cudaMemcpyAsync(unique_stamps, d_unique, sizeof(double) * groups, cudaMemcpyDeviceToHost, s));
+    NGICP_CUDA(h, cudaStreamSynchronize(s));
+    // keep the sorted keys (they define the groups) next to the sorted points
+    h->scan_keys = keys_sorted == keys_a ? keys_a : keys_b;
+    (keys_sorted == keys_a ? keys_a : keys_b) = nullptr;
+    h->scan_n = kept;
+    h->scan_groups = groups;
+  }
+  dev_free(d_recs, s); dev_free(keys_a, s); dev_free(keys_b, s); dev_free(vals_a, s); dev_free(vals_b, s);
+  dev_free(sort_scratch, s); dev_free(d_sums, s); dev_free(d_unique, s);
+  *n_unique = groups;
+  if (n_kept) *n_kept = kept;
+  return rc;
+}
+
+int ngicp_scan_deskew(ngicp_handle* p, const float* frames16, size_t n_frames, const float leaf[3], int set_as, float* out_xyz, size_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(p);
+  if (!h || !frames16 || !n_out) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_deskew: bad argument");
+  if (!h->scan_pts || h->scan_n == 0) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_deskew: no ingested scan (call ngicp_scan_ingest first)");
+  if (n_frames != 1 && n_frames != h->scan_groups)
+    return fail(h, NGICP_ERR_INVALID, "ngicp_scan_deskew: need one frame per unique time stamp (or exactly one frame for a rigid transform)");
+  if (set_as < -1 || set_as > 1) return fail(h, NGICP_ERR_INVALID, "ngicp_scan_deskew: set_as must be -1, 0 (source) or 1 (target)");
+  if (int rc = select_device(h)) return rc;
+  cudaStream_t s = h->stream;
+  const int n = (int)h->scan_n;
+  const int nb = (n + kFiltThreads - 1) / kFiltThreads;
+  float* d_frames = nullptr;
+  unsigned int* d_sums = nullptr;
+  float4* d_out = nullptr;
+  float4* d_vox = nullptr;
+  NGICP_CUDA(h, dev_alloc(&d_frames, n_frames * 16, s));
+  NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 2, s));
+  NGICP_CUDA(h, dev_alloc(&d_out, (size_t)n, s));
+  NGICP_CUDA(h, cudaMemcpyAsync(d_frames, frames16, sizeof(float) * 16 * n_frames, cudaMemcpyHostToDevice, s));
+  const unsigned long long seq = ++h->seq;
+  zero_u32_kernel<<<1, 1, 0, s>>>(d_sums + nb + 1);
+  ingest_count_kernel<<<nb, kFiltThreads, 0, s>>>(h->scan_keys, n, d_sums, d_sums + nb + 1);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
+  deskew_apply_kernel<<<nb, kFiltThreads, 0, s>>>(h->scan_pts, h->scan_keys, n, d_sums, d_frames, (int)n_frames, d_out);
+  count_launch(h, 4);
+  NGICP_CUDA(h, cudaGetLastError());
+  size_t groups = 0;
+  int rc = wait_count(h, seq, &groups);
+  const float* cur = reinterpret_cast<const float*>(d_out);
+  size_t cur_n = (size_t)n;
+  if (!rc && leaf) {
+    rc = voxel_grid_device(h, cur, 4, n, leaf, &d_vox, &cur_n, nullptr);
+    if (!rc) cur = reinterpret_cast<const float*>(d_vox);
+  }
+  if (!rc && out_xyz && cur_n > 0) {
+    float* d_o = nullptr;
+    NGICP_CUDA(h, dev_alloc(&d_o, cur_n * 3, s));
+    f4_to_xyz_kernel<<<((int)cur_n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4*>(cur), (int)cur_n, d_o);
+    count_launch(h);
+    NGICP_CUDA(h, cudaMemcpyAsync(out_xyz, d_o, cur_n * 12, cudaMemcpyDeviceToHost, s));
+    NGICP_CUDA(h, cudaStreamSynchronize(s));
+    dev_free(d_o, s);
+  }
+  if (!rc && set_as >= 0) {
+    Index* idx = nullptr;
+    rc = build_index(h, cur, 4, (int)cur_n, nullptr, 1, &idx);
+    if (!rc) rc = swap_in_index(h, set_as, idx);
+  }
+  NGICP_CUDA(h, cudaStreamSynchronize(s));   // frames16 is the caller's pageable buffer
+  *n_out = cur_n;
+  dev_free(d_frames, s); dev_free(d_sums, s); dev_free(d_out, s); dev_free(d_vox, s);
   return rc;
 }
 

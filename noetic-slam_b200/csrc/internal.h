@@ -63,6 +63,10 @@ struct ngicp_handle {
   unsigned int* heavy_count = nullptr;   // [2] list lengths, alternating between searches (the heavy kernel clears the next one)
   unsigned int heavy_parity = 0;
   size_t corr_n = 0;            // number of source points the cached correspondences belong to
+  // scan held between ngicp_scan_ingest and ngicp_scan_deskew (filters.cu): time-sorted, cropped, on the device
+  float4* scan_pts = nullptr;               // [scan_n] xyz1 in ascending time-stamp order
+  unsigned long long* scan_keys = nullptr;  // [scan_n] order-preserving integer image of the time stamps
+  size_t scan_n = 0, scan_groups = 0;
   double lin_pose[12];          // pose of the last linearize (R row-major 9 + t 3), needed by compute_error
   bool lin_valid = false;
   double* partials = nullptr;   // [max_blocks][32] block partial sums

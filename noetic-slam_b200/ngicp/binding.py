@@ -27,7 +27,7 @@ SYMBOLS = [
     "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
     "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances", "ngicp_set_input_batch", "ngicp_batch_linearize",
     "ngicp_keyframe_capture", "ngicp_keyframe_transform", "ngicp_keyframe_size", "ngicp_keyframe_release", "ngicp_keyframe_download",
-    "ngicp_submap_assemble", "ngicp_filter_scan",
+    "ngicp_submap_assemble", "ngicp_filter_scan", "ngicp_scan_ingest", "ngicp_scan_deskew",
     "ngicp_enable_timing", "ngicp_get_timings",
 ]
 
@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.ngicp_keyframe_download.argtypes = [vp, vp, fp, dp]
     L.ngicp_submap_assemble.argtypes = [vp, C.POINTER(vp), i]
     L.ngicp_filter_scan.argtypes = [vp, vp, sz, sz, fp, fp, i, fp, i, fp, C.POINTER(sz)]
+    L.ngicp_scan_ingest.argtypes = [vp, vp, sz, sz, sz, i, fp, fp, i, dp, C.POINTER(sz), C.POINTER(sz)]
+    L.ngicp_scan_deskew.argtypes = [vp, fp, sz, fp, i, fp, C.POINTER(sz)]
     L.ngicp_enable_timing.argtypes = [vp, i]
     L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
     _lib = L

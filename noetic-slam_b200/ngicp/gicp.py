@@ -195,6 +195,46 @@ class NanoGICP:
         self._input = out
         return out
 
+    def ingestScan(self, records: np.ndarray, time_field: str, crop=None):
+        """First half of dlio::OdomNode::deskewPointcloud (odom.cc:588-650) on the device: `records` is a structured
+        array with float32 x, y, z at offsets 0/4/8 and a per-point time stamp field (uint32 `t`, float32 `time` or
+        float64 `timestamp`). Drops non-finite points, applies the optional CropBox, sorts by time stamp and returns
+        (unique stamps ascending as float64 raw field values, points kept)."""
+        rec = np.ascontiguousarray(records)
+        dt = rec.dtype.fields[time_field][0]
+        ttype = {np.dtype(np.uint32): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[dt]
+        fp = C.POINTER(C.c_float)
+        if crop is not None:
+            mn = np.ascontiguousarray(crop[0], np.float32); mx = np.ascontiguousarray(crop[1], np.float32)
+            a_mn, a_mx, neg = mn.ctypes.data_as(fp), mx.ctypes.data_as(fp), int(bool(crop[2]))
+        else:
+            a_mn = a_mx = None; neg = 0
+        stamps = np.empty(len(rec), np.float64)
+        nu, nk = C.c_size_t(0), C.c_size_t(0)
+        B.check(self._h, self._L.ngicp_scan_ingest(self._h, rec.ctypes.data, len(rec), rec.dtype.itemsize, rec.dtype.fields[time_field][1], ttype,
+                                                   a_mn, a_mx, neg, stamps.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nu), C.byref(nk)))
+        self._ingested = nk.value
+        return stamps[:nu.value].copy(), nk.value
+
+    def deskewScan(self, frames, leaf=None, set_source=True):
+        """Second half (odom.cc:690-701, then :575-584 and :721): frames = (n_unique, 4, 4) float32 poses (already times the
+        extrinsic), or one (4, 4) matrix for the no-IMU paths. Returns the deskewed (and voxel-filtered) cloud."""
+        F = np.asarray(frames, np.float32)
+        if F.ndim == 2:
+            F = F[None]
+        Fc = np.ascontiguousarray(F.transpose(0, 2, 1)).reshape(-1, 16)        # column-major
+        lf = None if leaf is None else np.ascontiguousarray(leaf, np.float32)
+        fp = C.POINTER(C.c_float)
+        out = np.empty((self._ingested, 3), np.float32)
+        n_out = C.c_size_t(0)
+        B.check(self._h, self._L.ngicp_scan_deskew(self._h, Fc.ctypes.data_as(fp), len(Fc), None if lf is None else lf.ctypes.data_as(fp),
+                                                   B.SOURCE if set_source else -1, out.ctypes.data_as(fp), C.byref(n_out)))
+        out = out[:n_out.value].copy()
+        if set_source:
+            self.source_kdtree_ = KdTreeFLANN._adopt(self, self._L.ngicp_get_index(self._h, B.SOURCE), out)
+            self._input = out
+        return out
+
     def registerInputSource(self, cloud):  # nano_gicp.cc:119-124: stores the cloud only
         self._input = cloud
 

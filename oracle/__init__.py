@@ -81,6 +81,9 @@ def lib(variant: str = "port") -> C.CDLL:
     L.orc_gicp_update_correspondences.argtypes = [vp, dp, ip, fp, dp]
     L.orc_crop_box.restype = sz
     L.orc_crop_box.argtypes = [fp, sz, sz, fp, fp, i, fp]
+    L.orc_scan_ingest.restype = sz
+    L.orc_scan_ingest.argtypes = [vp, sz, sz, sz, i, fp, fp, i, fp, ip, dp, C.POINTER(sz)]
+    L.orc_scan_deskew.argtypes = [fp, ip, sz, fp, sz, fp]
     L.orc_voxel_grid.restype = sz
     L.orc_voxel_grid.argtypes = [fp, sz, sz, fp, fp, ip, ip]
     L.orc_gicp_num_correspondences.restype = i
@@ -293,3 +296,37 @@ class VoxelGrid:
                                    vox.ctypes.data_as(ip), cnt.ctypes.data_as(ip))
         self.voxel_index, self.voxel_count = vox[:m].copy(), cnt[:m].copy()
         return out[:m].copy()
+
+
+def scan_ingest(records: np.ndarray, time_field: str, crop=None, variant: str = "port"):
+    """dlio::OdomNode::deskewPointcloud, first half (oracle.cc:orc_scan_ingest): (xyz in time order, group per point,
+    unique stamps as raw field values)."""
+    L = lib(variant)
+    rec = np.ascontiguousarray(records)
+    dt = rec.dtype.fields[time_field][0]
+    ttype = {np.dtype(np.uint32): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[dt]
+    fp, ip, dp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
+    if crop is not None:
+        mn = np.ascontiguousarray(crop[0], np.float32); mx = np.ascontiguousarray(crop[1], np.float32)
+        a_mn, a_mx, neg = mn.ctypes.data_as(fp), mx.ctypes.data_as(fp), int(bool(crop[2]))
+    else:
+        a_mn = a_mx = None; neg = 0
+    xyz = np.empty((len(rec), 3), np.float32); grp = np.empty(len(rec), np.int32); st = np.empty(len(rec), np.float64)
+    nu = C.c_size_t(0)
+    m = L.orc_scan_ingest(rec.ctypes.data, len(rec), rec.dtype.itemsize, rec.dtype.fields[time_field][1], ttype, a_mn, a_mx, neg,
+                          xyz.ctypes.data_as(fp), grp.ctypes.data_as(ip), st.ctypes.data_as(dp), C.byref(nu))
+    return xyz[:m].copy(), grp[:m].copy(), st[:nu.value].copy()
+
+
+def scan_deskew(xyz, group, frames, variant: str = "port"):
+    """Second half (oracle.cc:orc_scan_deskew): frames = (n_unique, 4, 4) or one (4, 4) float32 matrix."""
+    L = lib(variant)
+    F = np.asarray(frames, np.float32)
+    if F.ndim == 2:
+        F = F[None]
+    Fc = np.ascontiguousarray(F.transpose(0, 2, 1)).reshape(-1, 16)
+    xyz = np.ascontiguousarray(xyz, np.float32); group = np.ascontiguousarray(group, np.int32)
+    out = np.empty_like(xyz)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.orc_scan_deskew(xyz.ctypes.data_as(fp), group.ctypes.data_as(ip), len(xyz), Fc.ctypes.data_as(fp), len(Fc), out.ctypes.data_as(fp))
+    return out

@@ -773,4 +773,53 @@ size_t orc_voxel_grid(const float* pts, size_t n, size_t stride_floats, const fl
   return m;
 }
 
+// ---- deskew: dlio::OdomNode::deskewPointcloud, odom.cc:588-706 ------------------------------------
+// ingest: drop non-finite points (:496-498), optional CropBox (:500-502), sort by the per-point time stamp (:634-635;
+// stable here, std::partial_sort_copy leaves ties unspecified), unique stamps (:638-650). Outputs: xyz in time order,
+// group (index of its unique stamp) per point, unique stamps as raw field values. Returns the number of points kept.
+size_t orc_scan_ingest(const unsigned char* recs, size_t n, size_t stride_bytes, size_t time_off, int time_type, const float* mn, const float* mx,
+                       int negative, float* out_xyz, int* out_group, double* unique_stamps, size_t* n_unique) {
+  struct Item { double stamp; size_t i; };
+  std::vector<Item> items;
+  items.reserve(n);
+  for (size_t i = 0; i < n; i++) {
+    const unsigned char* rec = recs + i * stride_bytes;
+    const float* p = reinterpret_cast<const float*>(rec);
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    if (mn && mx) {
+      const bool outside = (p[0] < mn[0] || p[1] < mn[1] || p[2] < mn[2]) || (p[0] > mx[0] || p[1] > mx[1] || p[2] > mx[2]);
+      if (!(outside ? (negative != 0) : (negative == 0))) continue;
+    }
+    double st;
+    if (time_type == 0) { std::uint32_t t; std::memcpy(&t, rec + time_off, 4); st = static_cast<double>(t); }
+    else if (time_type == 1) { float t; std::memcpy(&t, rec + time_off, 4); st = static_cast<double>(t); }
+    else { std::memcpy(&st, rec + time_off, 8); }
+    items.push_back({st, i});
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.stamp < b.stamp; });
+  size_t groups = 0;
+  for (size_t j = 0; j < items.size(); j++) {
+    if (j == 0 || items[j].stamp != items[j - 1].stamp) unique_stamps[groups++] = items[j].stamp;
+    const float* p = reinterpret_cast<const float*>(recs + items[j].i * stride_bytes);
+    out_xyz[3 * j] = p[0]; out_xyz[3 * j + 1] = p[1]; out_xyz[3 * j + 2] = p[2];
+    out_group[j] = static_cast<int>(groups - 1);
+  }
+  *n_unique = groups;
+  return items.size();
+}
+// pt = T_group * pt with w = 1 (odom.cc:690-701), fp32: ((m0 x + m1 y) + m2 z) + m3; frames16 column-major; n_frames == 1
+// applies the one matrix to every point (pcl::transformPointCloud, :659 / :681)
+void orc_scan_deskew(const float* xyz, const int* group, size_t n, const float* frames16, size_t n_frames, float* out) {
+  for (size_t j = 0; j < n; j++) {
+    const float* T = frames16 + (n_frames == 1 ? 0 : static_cast<size_t>(group[j])) * 16;
+    const float x = xyz[3 * j], y = xyz[3 * j + 1], z = xyz[3 * j + 2];
+    for (int r = 0; r < 3; r++) {
+      volatile float a = T[r] * x, b = T[4 + r] * y, c = T[8 + r] * z;   // volatile: no FMA contraction
+      volatile float s1 = a + b;
+      volatile float s2 = s1 + c;
+      out[3 * j + r] = s2 + T[12 + r];
+    }
+  }
+}
+
 }  // extern "C"

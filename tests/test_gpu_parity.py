@@ -541,3 +541,66 @@ def test_filtered_scan_becomes_the_source_without_leaving_the_device():
     Tg, To = g.align(), o.align()
     assert g.nr_iterations_ == o.nr_iterations_ and g.hasConverged() == o.hasConverged()
     assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(Tg[:3, :3], To[:3, :3]) < POSE_R_TOL
+
+
+# ----------------------------------------------------------------------------------- f-3: deskew
+def _timed_scan(seed, time_dtype, n_cols=512):
+    """A scan as a structured point record with a per-point time stamp (columns of a spinning LiDAR share a stamp)."""
+    a, _, _ = S.scan_pair(seed, w=256)
+    rng = np.random.default_rng(seed)
+    name = {np.uint32: "t", np.float32: "time", np.float64: "timestamp"}[time_dtype]
+    rec = np.zeros(len(a), dtype=np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("pad", "<f4"), ("intensity", "<f4"), (name, time_dtype), ("ring", "<u2")],
+                                           align=True))
+    rec["x"], rec["y"], rec["z"] = a[:, 0], a[:, 1], a[:, 2]
+    col = rng.integers(0, n_cols, len(a))                       # arrival order is NOT time order
+    if time_dtype is np.uint32:
+        rec[name] = (col * 48828).astype(np.uint32)             # ns offsets inside a 25 ms sweep
+    elif time_dtype is np.float32:
+        rec[name] = (col * 4.8828e-5 - 0.0125).astype(np.float32)   # seconds, negative first half like Velodyne drivers
+    else:
+        rec[name] = 1.7e9 + col * 4.8828e-5
+    rec["x"][::131] = np.nan
+    return rec, name
+
+
+def _group_frames(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.stack([synth.se3(tuple(rng.normal(0, 0.05, 3)), tuple(rng.normal(0, 1.0, 3))) for _ in range(n)]).astype(np.float32)
+
+
+@pytest.mark.parametrize("time_dtype", [np.uint32, np.float32, np.float64])
+def test_deskew_matches_the_restated_reference(gicp, time_dtype):
+    rec, name = _timed_scan(3, time_dtype)
+    crop = ([-1.0] * 3, [1.0] * 3, True)
+    stamps, kept = gicp.ingestScan(rec, name, crop=crop)
+    xyz_o, grp_o, stamps_o = oracle.scan_ingest(rec, name, crop=crop)
+    assert kept == len(xyz_o) and (stamps == stamps_o).all() and (np.diff(stamps) > 0).all()
+    frames = _group_frames(len(stamps))
+    out = gicp.deskewScan(frames, leaf=None, set_source=False)
+    ref = oracle.scan_deskew(xyz_o, grp_o, frames)
+    assert out.shape == ref.shape and (out == ref).all()         # same order (time, then arrival), same fp32 arithmetic
+    one = gicp.deskewScan(frames[7], leaf=None, set_source=False)       # the no-IMU paths: one rigid transform for the whole scan
+    assert (one == oracle.scan_deskew(xyz_o, grp_o, frames[7])).all()
+    with pytest.raises(ngicp.NgicpError):
+        gicp.deskewScan(frames[:5], set_source=False)            # frames.size() != timestamps.size() (odom.cc:677)
+
+
+def test_deskewed_voxel_filtered_scan_registers_like_the_host_pipeline():
+    """ingest -> deskew -> VoxelGrid -> setInputSource on the device == the same chain restated on the CPU feeding the oracle."""
+    rec, name = _timed_scan(5, np.uint32)
+    _, b, _ = S.scan_pair(5, w=256)
+    g = S.configure(ngicp.NanoGICP(0)); o = S.configure(oracle.OracleGICP("port"))
+    crop = ([-1.0] * 3, [1.0] * 3, True)
+    stamps, kept = g.ingestScan(rec, name, crop=crop)
+    frames = np.stack([synth.se3((1e-4 * i, 0.0, 0.0), (0.0, 0.0, 2e-3 * i)) for i in range(len(stamps))]).astype(np.float32)   # a gentle sweep motion
+    src = g.deskewScan(frames, leaf=(0.25, 0.25, 0.25), set_source=True)
+    xyz_o, grp_o, _ = oracle.scan_ingest(rec, name, crop=crop)
+    ov = oracle.VoxelGrid(); ov.setLeafSize(0.25); ov.setInputCloud(oracle.scan_deskew(xyz_o, grp_o, frames))
+    ref = ov.filter()
+    assert src.shape == ref.shape and (src == ref).all()
+    o.setInputSource(ref)
+    for x in (g, o):
+        x.setInputTarget(b); x.calculateSourceCovariances(); x.calculateTargetCovariances()
+    Tg, To = g.align(), o.align()
+    assert g.nr_iterations_ == o.nr_iterations_
+    assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(Tg[:3, :3], To[:3, :3]) < POSE_R_TOL
