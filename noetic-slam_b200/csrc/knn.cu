@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
 
 // Production K2: a warp owns 32/LPQ consecutive (Morton-sorted) points, LPQ lanes per point, shared staged
 // candidates (wknn.cuh).
-constexpr int kSelfWarps = 4;
+constexpr int kSelfWarps = 1;
 template <int K, int LPQ>
 __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int cmax, int normalization,
                                                                         int* __restrict__ nbr, double* __restrict__ dens_term) {

@@ -39,6 +39,7 @@ struct __align__(16) WarpScratch {
   uint32_t rstart[128];         // non-empty voxel buckets of the block (<= 64) or ball (<= 125), compacted, in scan order
   uint32_t rpre[129];           // exclusive prefix of their sizes; rpre[R] = M
   uint32_t pad[3];
+  unsigned char rcode[128];     // block mode: cell id (0..63, scan order) of every compacted bucket, for box-distance pruning
   unsigned long long mbar[2];   // one mbarrier per buffer: the bulk copies complete on it
   float4 qm[8];                 // member queries of the current pass (k = 1 path)
 };
@@ -227,8 +228,8 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     const unsigned nz0 = __ballot_sync(FULL, cnt[0] != 0), nz1 = __ballot_sync(FULL, cnt[1] != 0);
     const unsigned lt = (1u << lane) - 1u;
     const int R = __popc(nz0) + __popc(nz1);
-    if (cnt[0]) { const int i0 = __popc(nz0 & lt); ws.rstart[i0] = st[0]; ws.rpre[i0] = inc0 - cnt[0]; }
-    if (cnt[1]) { const int i1 = __popc(nz0) + __popc(nz1 & lt); ws.rstart[i1] = st[1]; ws.rpre[i1] = tot0 + inc1 - cnt[1]; }
+    if (cnt[0]) { const int i0 = __popc(nz0 & lt); ws.rstart[i0] = st[0]; ws.rpre[i0] = inc0 - cnt[0]; ws.rcode[i0] = (unsigned char)lane; }
+    if (cnt[1]) { const int i1 = __popc(nz0) + __popc(nz1 & lt); ws.rstart[i1] = st[1]; ws.rpre[i1] = tot0 + inc1 - cnt[1]; ws.rcode[i1] = (unsigned char)(lane + 32); }
     if (lane == 0) ws.rpre[R] = M;
     __syncwarp();
     if (member) best.reset();
@@ -356,7 +357,33 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           constexpr int kQs = (TK::kK + LPQ - 1) / LPQ - 1;          // shared: LPQ lanes per query
           constexpr int kQh = (TK::kK + 31) / 32 - 1;                // heavy: 32 lanes per query
           float lim = __int_as_float(0x7f800000);
+          // Big passes (a sparse group cell next to a dense one: thousands of staged candidates, nearly all of them far
+          // from every member) skip whole chunks: a chunk that lies inside one or two voxel buckets is scanned only if
+          // some scanning lane's bound reaches the box of one of them.
+          const bool prune = M > 1024u;
+          const float pux = heavy ? __shfl_sync(FULL, ux, mi) : ux, puy = heavy ? __shfl_sync(FULL, uy, mi) : uy, puz = heavy ? __shfl_sync(FULL, uz, mi) : uz;
+          const float phL = h0 * (float)(1 << Lg);
+          int rb = 0;
           WKNN_FOR_CHUNKS({
+            if (prune && c0 > 0) {
+              while (ws.rpre[rb + 1] <= c0) rb++;                                   // first bucket of this chunk (uniform)
+              const int re = ws.rpre[rb + 1] >= c0 + (uint32_t)nch ? rb : ((rb + 2 <= R && ws.rpre[rb + 2] >= c0 + (uint32_t)nch) ? rb + 1 : -1);
+              if (re >= 0) {
+                bool need = false;
+                for (int bi = rb; bi <= re; bi++) {
+                  const int ci = ws.rcode[bi];
+                  const int ox = (ci & 8) ? ((ci & 1) ? 2 : -1) : (ci & 1), oy = (ci & 16) ? ((ci & 2) ? 2 : -1) : ((ci >> 1) & 1),
+                            oz = (ci & 32) ? ((ci & 4) ? 2 : -1) : ((ci >> 2) & 1);
+                  const float slack = 2.0f * margin;
+                  const float ax = (float)(2 * lpx + ox) * phL, ay = (float)(2 * lpy + oy) * phL, az = (float)(2 * lpz + oz) * phL;
+                  const float ex = fmaxf(fmaxf(ax - slack - pux, pux - (ax + phL + slack)), 0.0f);
+                  const float ey = fmaxf(fmaxf(ay - slack - puy, puy - (ay + phL + slack)), 0.0f);
+                  const float ez = fmaxf(fmaxf(az - slack - puz, puz - (az + phL + slack)), 0.0f);
+                  need |= !((ex * ex + ey * ey + ez * ez) * 0.999999f > fminf(lim, part.worst()));
+                }
+                if (!__any_sync(FULL, scan && need)) continue;                      // next chunk (the macro's loop)
+              }
+            }
             int e_first = s0;
             if (c0 == 0) {
               // seed: the first KP candidates of this lane's share, sorted by a network instead of inserted one by one
