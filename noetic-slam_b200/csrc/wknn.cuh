@@ -22,6 +22,7 @@
 namespace ngicp {
 
 constexpr int kWarpChunk = 256;  // candidates staged per pass and warp
+constexpr int kPruneStaged = 1024;  // passes that stage more candidates than this first drop the voxel buckets no member can need
 
 #ifdef NGICP_STATS
 // development counters: [0] passes, [1] staged candidates, [2] member lanes, [3] warp_knn calls, [4] refused members
@@ -327,7 +328,6 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
       // lanes are then merged by log2(width) bitonic steps (exchange with the xor partner, keep the K smallest of the
       // two sorted lists as a bitonic sequence, re-sort it with the half-cleaner network). Deliberately ONE code site
       // for the insertion and ONE for the merge: this kernel used to be 138 KB of SASS and stalled on instruction fetch.
-      const bool heavy = LPQ == 1 ? false : (long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M;
       if (LPQ == 1) {
         WKNN_FOR_CHUNKS({
           if (member) {
@@ -340,6 +340,17 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           }
         })
       } else {
+        // Big passes (a sparse group cell next to a dense one: thousands of staged candidates, nearly all of them far
+        // from every member) run twice. Phase 0 scans only the first chunk — the group cell's own children come first
+        // in scan order — which gives every member a valid bound on its k-th distance; the voxel buckets that no
+        // member's bound reaches (box distance) are then dropped from the staging list and phase 1 is the normal scan,
+        // from scratch, over what is left. Same result: a dropped bucket cannot hold any member's k nearest.
+        uint32_t Mf = M;
+        int Rf = R;
+        for (int ph = (M > (uint32_t)kPruneStaged) ? 0 : 1; ph < 2; ph++) {
+        const uint32_t M = ph == 0 ? (uint32_t)kWarpChunk : Mf;      // (shadow the pass totals: the chunk loop reads M and R)
+        const int R = Rf;
+        const bool heavy = ph == 0 ? false : (long long)nmem * (2ll * M + 1000) < (long long)(60 / LPQ) * M;
         const int width = heavy ? 32 : LPQ;
         const int s0 = lane & (width - 1);
         unsigned rem = heavy ? mem_mask : 1u;
@@ -357,33 +368,7 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           constexpr int kQs = (TK::kK + LPQ - 1) / LPQ - 1;          // shared: LPQ lanes per query
           constexpr int kQh = (TK::kK + 31) / 32 - 1;                // heavy: 32 lanes per query
           float lim = __int_as_float(0x7f800000);
-          // Big passes (a sparse group cell next to a dense one: thousands of staged candidates, nearly all of them far
-          // from every member) skip whole chunks: a chunk that lies inside one or two voxel buckets is scanned only if
-          // some scanning lane's bound reaches the box of one of them.
-          const bool prune = M > 1024u;
-          const float pux = heavy ? __shfl_sync(FULL, ux, mi) : ux, puy = heavy ? __shfl_sync(FULL, uy, mi) : uy, puz = heavy ? __shfl_sync(FULL, uz, mi) : uz;
-          const float phL = h0 * (float)(1 << Lg);
-          int rb = 0;
           WKNN_FOR_CHUNKS({
-            if (prune && c0 > 0) {
-              while (ws.rpre[rb + 1] <= c0) rb++;                                   // first bucket of this chunk (uniform)
-              const int re = ws.rpre[rb + 1] >= c0 + (uint32_t)nch ? rb : ((rb + 2 <= R && ws.rpre[rb + 2] >= c0 + (uint32_t)nch) ? rb + 1 : -1);
-              if (re >= 0) {
-                bool need = false;
-                for (int bi = rb; bi <= re; bi++) {
-                  const int ci = ws.rcode[bi];
-                  const int ox = (ci & 8) ? ((ci & 1) ? 2 : -1) : (ci & 1), oy = (ci & 16) ? ((ci & 2) ? 2 : -1) : ((ci >> 1) & 1),
-                            oz = (ci & 32) ? ((ci & 4) ? 2 : -1) : ((ci >> 2) & 1);
-                  const float slack = 2.0f * margin;
-                  const float ax = (float)(2 * lpx + ox) * phL, ay = (float)(2 * lpy + oy) * phL, az = (float)(2 * lpz + oz) * phL;
-                  const float ex = fmaxf(fmaxf(ax - slack - pux, pux - (ax + phL + slack)), 0.0f);
-                  const float ey = fmaxf(fmaxf(ay - slack - puy, puy - (ay + phL + slack)), 0.0f);
-                  const float ez = fmaxf(fmaxf(az - slack - puz, puz - (az + phL + slack)), 0.0f);
-                  need |= !((ex * ex + ey * ey + ez * ez) * 0.999999f > fminf(lim, part.worst()));
-                }
-                if (!__any_sync(FULL, scan && need)) continue;                      // next chunk (the macro's loop)
-              }
-            }
             int e_first = s0;
             if (c0 == 0) {
               // seed: the first KP candidates of this lane's share, sorted by a network instead of inserted one by one
@@ -414,6 +399,59 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
           for (int off = 1; off < width; off <<= 1) part.merge_with_partner(off);
           const bool take = heavy ? ((lane & ~(LPQ - 1)) == (mi & ~(LPQ - 1))) : member;
           if (take) part.store(best);
+        }
+        if (ph == 0) {
+          // ---- drop the buckets no member can need; two buckets per lane as at staging time
+          uint32_t bs[2], bc[2];
+          int bcode[2];
+          bool need[2];
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int bi = lane + 32 * half;
+            const bool valid = bi < Rf;
+            bs[half] = valid ? ws.rstart[bi] : 0u;
+            bc[half] = valid ? ws.rpre[bi + 1] - ws.rpre[bi] : 0u;
+            bcode[half] = valid ? (int)ws.rcode[bi] : 0;
+            need[half] = false;
+          }
+          const float my_bound = best.worst();
+          const float phL = h0 * (float)(1 << Lg), slack = 2.0f * margin;
+          for (int sl = 0; sl < 32 / LPQ; sl++) {
+            const int src = sl * LPQ;
+            if (!((mem_mask >> src) & 1u)) continue;                                // uniform
+            const float bux = __shfl_sync(FULL, ux, src), buy = __shfl_sync(FULL, uy, src), buz = __shfl_sync(FULL, uz, src);
+            const float bb = __shfl_sync(FULL, my_bound, src);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+              const int ci = bcode[half];
+              const int ox = (ci & 8) ? ((ci & 1) ? 2 : -1) : (ci & 1), oy = (ci & 16) ? ((ci & 2) ? 2 : -1) : ((ci >> 1) & 1),
+                        oz = (ci & 32) ? ((ci & 4) ? 2 : -1) : ((ci >> 2) & 1);
+              const float ax = (float)(2 * lpx + ox) * phL, ay = (float)(2 * lpy + oy) * phL, az = (float)(2 * lpz + oz) * phL;
+              const float ex = fmaxf(fmaxf(ax - slack - bux, bux - (ax + phL + slack)), 0.0f);
+              const float ey = fmaxf(fmaxf(ay - slack - buy, buy - (ay + phL + slack)), 0.0f);
+              const float ez = fmaxf(fmaxf(az - slack - buz, buz - (az + phL + slack)), 0.0f);
+              need[half] |= !((ex * ex + ey * ey + ez * ez) * 0.999999f > bb);
+            }
+          }
+          __syncwarp();
+          const uint32_t k0 = (need[0] && bc[0]) ? bc[0] : 0u, k1 = (need[1] && bc[1]) ? bc[1] : 0u;
+          uint32_t i0 = k0, i1 = k1;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULL, i0, off), b = __shfl_up_sync(FULL, i1, off);
+            if (lane >= off) { i0 += a; i1 += b; }
+          }
+          const uint32_t t0 = __shfl_sync(FULL, i0, 31);
+          const unsigned z0 = __ballot_sync(FULL, k0 != 0), z1 = __ballot_sync(FULL, k1 != 0);
+          const unsigned ltm = (1u << lane) - 1u;
+          if (k0) { const int w = __popc(z0 & ltm); ws.rstart[w] = bs[0]; ws.rpre[w] = i0 - k0; ws.rcode[w] = (unsigned char)bcode[0]; }
+          __syncwarp();   // the first half's compacted slots all lie below the second half's sources read above: order the writes anyway
+          if (k1) { const int w = __popc(z0) + __popc(z1 & ltm); ws.rstart[w] = bs[1]; ws.rpre[w] = t0 + i1 - k1; ws.rcode[w] = (unsigned char)bcode[1]; }
+          Rf = __popc(z0) + __popc(z1);
+          Mf = t0 + __shfl_sync(FULL, i1, 31);
+          if (lane == 0) ws.rpre[Rf] = Mf;
+          __syncwarp();
+        }
         }
       }
     }

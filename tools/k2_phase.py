@@ -1,4 +1,4 @@
-"""Development: where K2 warps spend their cycles (needs a -DNGICP_STATS build)."""
+"""Development: the slowest K2 work items and what they did (needs a -DNGICP_STATS build)."""
 import sys, ctypes
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -7,17 +7,18 @@ for p in (str(ROOT), str(ROOT / "noetic-slam_b200"), str(ROOT / "tests")):
 import numpy as np
 import bench, ngicp
 L = ngicp.lib()
-def phase():
-    out = (ctypes.c_ulonglong * 40)()
-    L.ngicp_debug_phase_knn(out, 1)
-    return list(out)
 tgt, bounds, scans = bench.make_workload(0)
 g = bench.configure(ngicp.NanoGICP(0))
 g.setInputSource(scans[0]); g.calculateSourceCovariances()
-for i in (1, 2):
-    phase()
-    g.setInputSource(scans[i]); g.calculateSourceCovariances()
-    p = phase()
-    tot = p[2]
-    print(f"scan {i}: cycles/warp {tot // 8192}  heavy rounds {100 * p[0] / tot:.1f}%  shared rounds {100 * p[1] / tot:.1f}%")
-    print("   per-warp cycles histogram:", {f"<2^{b + 1}": p[8 + b] for b in range(32) if p[8 + b]})
+g.setInputSource(scans[1]); g.calculateSourceCovariances()
+buf = (ctypes.c_uint * (8 * 8192))()
+L.ngicp_debug_items_knn(buf, 8192)
+a = np.array(buf[:], dtype=np.int64).reshape(8192, 8)
+names = ["cycles", "passes", "sumM", "maxM", "heavy_rounds", "refused", "skipped", "chunks"]
+print("mean", dict(zip(names, a.mean(0).round(1))))
+order = np.argsort(-a[:, 0])
+for i in order[:12]:
+    print(int(i), dict(zip(names, a[i].tolist())))
+print("cycles percentiles 50/90/99/99.9/max", np.percentile(a[:, 0], [50, 90, 99, 99.9, 100]).astype(int).tolist())
+big = a[:, 0] > 100000
+print("items > 100k cycles:", int(big.sum()), "share of all cycles", round(a[big, 0].sum() / a[:, 0].sum(), 3), "mean passes", a[big, 1].mean().round(2), "mean sumM", a[big, 2].mean().round(0), "mean heavy rounds", a[big, 4].mean().round(2))
