@@ -14,7 +14,7 @@ g.setInputSource(scans[1]); g.calculateSourceCovariances()
 buf = (ctypes.c_uint * (8 * 8192))()
 L.ngicp_debug_items_knn(buf, 8192)
 a = np.array(buf[:], dtype=np.int64).reshape(8192, 8)
-names = ["cycles", "passes", "sumM", "maxM", "heavy_rounds", "refused", "skipped", "chunks"]
+names = ["cycles", "passes", "sumM", "maxM", "heavy_rounds", "refused", "M_after_filter", "chunks"]
 print("mean", dict(zip(names, a.mean(0).round(1))))
 order = np.argsort(-a[:, 0])
 for i in order[:12]:
