@@ -314,6 +314,8 @@ def run_gpu(args, rank, local_rank, world):
     bulk = bulk_covariance(g, scans, hbm)
     bulk.update(bulk_linearize(g, scans, hbm))
     bulk.update(prefilter_probe(g, pinned, h_scans, world == 1))
+    if world == 1:
+        bulk.update(multi_sequence_probe(g, tgt, m4, d_scans, local_rank))
 
     # ---- CPU baseline beside it (bounded sample, all host cores) — rank 0 at N=1 only
     cpu = None
@@ -368,6 +370,44 @@ def bulk_covariance(g, scans, hbm, n_keyframes=64):
     out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": ncu_traffic("bulk_K3"),
                           "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
     return out
+
+
+def multi_sequence_probe(g, tgt, m4, d_scans, device, sequences=4, steps=24):
+    """Capacity of ONE GPU when several independent sequences (robots / replays) register against the same resident
+    submap at once: one handle + stream + host thread per sequence, the target tree shared (DLIO hands trees between
+    NanoGICP objects the same way, odom.cc:992-998). A single sequence is latency-bound (the LM loop is serial), so the
+    aggregate is what the hardware can actually sustain. Reported beside the headline, never instead of it."""
+    import ngicp
+    handles = [g]
+    for _ in range(sequences - 1):
+        h = configure(ngicp.NanoGICP(device))
+        h.registerInputTarget(tgt)
+        h.setTargetTree(g.target_kdtree_)
+        h.setTargetCovariances(m4)
+        handles.append(h)
+    for h in handles:                                   # warm every handle (allocations, first-use costs)
+        for i in range(2):
+            ds = d_scans[i % len(d_scans)]
+            h.setInputSourceDevice(ds.data_ptr(), ds.shape[0], token=ds); h.calculateSourceCovariances(); h.align()
+    start = threading.Barrier(sequences + 1)
+
+    def worker(h, k):
+        start.wait()
+        for i in range(steps):
+            ds = d_scans[(i + k) % len(d_scans)]
+            h.setInputSourceDevice(ds.data_ptr(), ds.shape[0], token=ds); h.calculateSourceCovariances(); h.align()
+        h.synchronize()
+
+    ths = [threading.Thread(target=worker, args=(h, k)) for k, h in enumerate(handles)]
+    for t in ths:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"multi_sequence": {"sequences": sequences, "scans_per_s": sequences * steps / dt, "note": "wall clock, no L2 flush, device-resident scans; "
+                               "independent sequences on one GPU sharing the resident submap"}}
 
 
 def prefilter_probe(g, pinned, h_scans, with_cpu):

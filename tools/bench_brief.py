@@ -7,3 +7,4 @@ b = d["bulk"]
 print("bulk: index", round(b["index_ms"], 3), "knn", round(b["knn_ms"], 3), "cov", round(b["covariance_ms"], 4), "K3 frac", round(b["roofline_K3"]["frac"], 3),
       "batch corr", round(b["batch_correspond_ms"], 3), "batch lin", round(b["batch_linearize_ms"], 4), "K4b frac", round(b["roofline_K4b"]["frac"], 3))
 print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in b.items() if k.startswith("prefilter")})
+print(b.get("multi_sequence"))
