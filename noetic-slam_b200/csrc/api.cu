@@ -217,6 +217,7 @@ int ngicp_create(int device, ngicp_handle** out) {
   if (const char* e = std::getenv("NGICP_K2_LPQ")) h->k2_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_LPQ")) h->k4_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_BALL")) h->k4_ball = std::atoi(e);
+  if (const char* e = std::getenv("NGICP_K4_SPEC")) h->k4_spec = std::atoi(e);
   for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // setIdentity, lsq_registration.cc:65
 #define CREATE_CUDA(expr)                                                                     \
   do {                                                                                        \
@@ -258,8 +259,13 @@ int ngicp_destroy(ngicp_handle* p) {
     release_index(h, h->index[w]);
     h->index[w] = nullptr;
   }
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   cudaStreamSynchronize(h->stream);
   if (h->corr) cudaFree(h->corr);
+  if (h->corr_alt) cudaFree(h->corr_alt);
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_spec) cudaEventDestroy(h->ev_spec);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->scan_pts) cudaFree(h->scan_pts);
   if (h->scan_keys) cudaFree(h->scan_keys);
   if (h->heavy) cudaFree(h->heavy);
@@ -441,6 +447,7 @@ extern "C++" {
 namespace ngicp {
 int swap_in_index(Handle* h, int which, Index* idx) {
   // same stream as everything else this handle does: no synchronisation needed to swap
+  drop_speculation(h);
   Index* old = h->index[which];
   h->index[which] = idx;
   if (old) {
@@ -624,6 +631,10 @@ int ngicp_align(ngicp_handle* p, const float guess[16], float T_out[16], int* nr
         const lm::Iso xi = lm::compose(delta, x0);
         double yi = 0.0, Ti[16];
         lm::to_colmajor(xi, Ti);
+        // if this trial is accepted and the loop goes on, the next linearize needs the correspondences at xi: search
+        // them on the second stream while K5 runs
+        if (i + 1 < prm.max_iterations && !lm::is_converged(delta, prm.rotation_epsilon, prm.transformation_epsilon))
+          if (int rc = speculate_search(h, Ti)) return rc;
         if (int rc = compute_error_device(h, Ti, &yi)) return rc;
         double den = 0.0;
         for (int j = 0; j < 6; j++) den += d[j] * (h->lm_lambda * d[j] - b[j]);
@@ -645,6 +656,7 @@ int ngicp_align(ngicp_handle* p, const float guess[16], float T_out[16], int* nr
     if (!step_ok) { status = NGICP_ERR_LM_NOT_CONVERGED; fail(h, status, "lm not converged!!"); break; }
     conv = lm::is_converged(delta, prm.rotation_epsilon, prm.transformation_epsilon);
   }
+  drop_speculation(h);
   if (T_out) {
     std::memset(T_out, 0, 16 * sizeof(float));
     for (int r = 0; r < 3; r++) {

@@ -59,6 +59,13 @@ struct ngicp_handle {
   // registration scratch
   int* corr = nullptr;          // [n_src] target sorted position or -1 (order: source sorted position)
   size_t corr_cap = 0;
+  // speculative correspondence search (linearize.cu:speculate_search): second stream, alternate result buffer
+  int* corr_alt = nullptr;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_spec = nullptr;
+  bool spec_pending = false;
+  double spec_T[16];
+  int k4_spec = 1;              // NGICP_K4_SPEC=0 disables
   void* heavy = nullptr;        // [corr_cap] HeavyQuery (linearize.cu): the queries the fast search kernel deferred
   unsigned int* heavy_count = nullptr;   // [2] list lengths, alternating between searches (the heavy kernel clears the next one)
   unsigned int heavy_parity = 0;
@@ -136,6 +143,8 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
 int compute_error_device(Handle* h, const double T[16], double* err);
 int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs);
 int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr);
+int speculate_search(Handle* h, const double T[16]);
+void drop_speculation(Handle* h);
 int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out);
 
 // bookkeeping shared with keyframe.cu

@@ -13,6 +13,7 @@
 // compute_error does not cache the Mahalanobis matrices: it rebuilds them from the pose of the last
 // linearize with the very same device function, so both kernels see bit-identical M.
 #include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 #include "linearize.cuh"
@@ -208,7 +209,8 @@ struct __align__(16) HeavyQuery {
 template <bool USE_PREV>
 __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView src, GridView tgt, PoseArg pose0, const PoseArg* __restrict__ poses,
                                                                        const int* __restrict__ target_seg, double thr2, float max_sqd,
-                                                                       int* __restrict__ corr, HeavyQuery* __restrict__ heavy, unsigned int* __restrict__ heavy_count) {
+                                                                       const int* corr_in, int* corr, HeavyQuery* __restrict__ heavy,
+                                                                       unsigned int* __restrict__ heavy_count) {
   const PoseArg P = load_pose(pose0, poses);
   const int b = blockIdx.y;
   const int begin = src.n_seg > 1 ? __ldg(src.seg_start + b) : 0;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kLinThreads) correspond_fast_kernel(GridView s
       transform_query(P, pa, qf);
       bool have = false;
       if (USE_PREV) {
-        const int prev = corr_hint(corr[j]);
+        const int prev = corr_hint(corr_in[j]);   // hints may live in another buffer than the results (speculative search)
         if (prev >= 0) {
           const float4 pb0 = __ldg(tgt.pts + prev);
           have = true;
@@ -512,10 +514,13 @@ static int check_ready(Handle* h) {
 
 static int ensure_corr(Handle* h, size_t n) {
   if (h->corr_cap >= n) return NGICP_OK;
+  drop_speculation(h);
   if (h->corr) NGICP_CUDA(h, cudaFree(h->corr));
+  if (h->corr_alt) NGICP_CUDA(h, cudaFree(h->corr_alt));
   if (h->heavy) NGICP_CUDA(h, cudaFree(h->heavy));
-  h->corr = nullptr; h->heavy = nullptr; h->corr_cap = 0;
+  h->corr = nullptr; h->corr_alt = nullptr; h->heavy = nullptr; h->corr_cap = 0;
   NGICP_CUDA(h, cudaMalloc(&h->corr, sizeof(int) * n));
+  NGICP_CUDA(h, cudaMalloc(&h->corr_alt, sizeof(int) * n));
   NGICP_CUDA(h, cudaMalloc(&h->heavy, sizeof(HeavyQuery) * n));
   if (!h->heavy_count) {
     NGICP_CUDA(h, cudaMalloc(&h->heavy_count, sizeof(unsigned int) * 2));
@@ -534,8 +539,9 @@ static int search_blocks_for(int n, int lpq) {
 
 // K4 = correspondence search + fused linearisation over n_scans source segments (n_scans = 1: the reference's
 // linearize). Poses, target segments and per-scan results live in device / host-mapped arrays when batched.
-static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const PoseArg* d_poses, const int* d_target_seg, bool want_Hb,
-                            double* partials, unsigned long long seq) {
+// the two search kernels of K4a on `stream`: hints from corr_in (if use_prev), results to corr_out
+static void launch_search(Handle* h, cudaStream_t stream, int n_scans, const PoseArg& P0, const PoseArg* d_poses, const int* d_target_seg, bool use_prev,
+                          const int* corr_in, int* corr_out) {
   const Index* si = h->index[0];
   const Index* ti = h->index[1];
   const double thr = h->params.max_corr_dist;
@@ -543,23 +549,35 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   const int per_scan = si->n / n_scans + 1;
   const dim3 sgrid(search_blocks_for(per_scan, 4), n_scans);
   const int hgrid = 148 * 5;   // heavy queries: one warp each, persistent over the list
+  unsigned int* cnt = h->heavy_count + (h->heavy_parity & 1u);
+  unsigned int* cnt_next = h->heavy_count + ((h->heavy_parity + 1u) & 1u);
+  h->heavy_parity++;
+  if (use_prev)
+    correspond_fast_kernel<true><<<sgrid, kLinThreads, 0, stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), corr_in, corr_out,
+                                                                    static_cast<HeavyQuery*>(h->heavy), cnt);
+  else
+    correspond_fast_kernel<false><<<sgrid, kLinThreads, 0, stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), corr_in, corr_out,
+                                                                     static_cast<HeavyQuery*>(h->heavy), cnt);
+  correspond_heavy_kernel<<<hgrid, kLinThreads, 0, stream>>>(ti->view(), thr2, max_sqd_for(thr), h->k4_cmax, corr_out, static_cast<const HeavyQuery*>(h->heavy), cnt,
+                                                             cnt_next);
+  count_launch(h, 2);
+}
+
+// K4 = correspondence search + fused linearisation over n_scans source segments (n_scans = 1: the reference's
+// linearize). Poses, target segments and per-scan results live in device / host-mapped arrays when batched.
+// search_done: h->corr already holds the correspondences for this pose (speculative search, see speculate_search).
+static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const PoseArg* d_poses, const int* d_target_seg, bool want_Hb,
+                            double* partials, unsigned long long seq, bool search_done = false) {
+  const Index* si = h->index[0];
+  const int per_scan = si->n / n_scans + 1;
   // batched: few fat blocks per scan (many points per thread amortise the 29-term block reduction); single scan: wide
   const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * 8) / n_scans)), n_scans);
   // the correspondences of the previous linearize (same clouds) seed this one
   const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
-  unsigned int* cnt = h->heavy_count + (h->heavy_parity & 1u);
-  unsigned int* cnt_next = h->heavy_count + ((h->heavy_parity + 1u) & 1u);
-  h->heavy_parity++;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-  if (use_prev)
-    correspond_fast_kernel<true><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
-                                                                       static_cast<HeavyQuery*>(h->heavy), cnt);
-  else
-    correspond_fast_kernel<false><<<sgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), P0, d_poses, d_target_seg, thr2, max_sqd_for(thr), h->corr,
-                                                                        static_cast<HeavyQuery*>(h->heavy), cnt);
-  correspond_heavy_kernel<<<hgrid, kLinThreads, 0, h->stream>>>(ti->view(), thr2, max_sqd_for(thr), h->k4_cmax, h->corr,
-                                                                static_cast<const HeavyQuery*>(h->heavy), cnt, cnt_next);
+  if (!search_done) launch_search(h, h->stream, n_scans, P0, d_poses, d_target_seg, use_prev, h->corr, h->corr);
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+  const Index* ti = h->index[1];
   if (want_Hb)
     linearize_kernel<true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
                                                                 h->counter, h->slot_dev, seq);
@@ -567,7 +585,7 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
     linearize_kernel<false><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
                                                                  h->counter, h->slot_dev, seq);
   h->corr_n = (size_t)si->n;
-  count_launch(h, 3);
+  count_launch(h, 1);
   NGICP_CUDA(h, cudaGetLastError());
   if (h->timing) cudaEventRecord(h->ev[1], h->stream);
   if (int rc = wait_slot(h, n_scans, seq)) return rc;
@@ -581,6 +599,36 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   }
   h->t.linearize_calls++;
   return NGICP_OK;
+}
+
+// While K5 evaluates a trial pose on the main stream, search the correspondences AT that pose on a second stream: if
+// the LM step is accepted (the usual case) the next linearize starts with its search already done. Hints come from the
+// current correspondences (read-only here and in K5), results go to the alternate buffer; nothing is consumed unless
+// the next linearize asks for exactly this pose.
+int speculate_search(Handle* h, const double T[16]) {
+  const Index* si = h->index[0];
+  if (!h->k4_spec || h->timing || !h->lin_valid || !h->corr_alt || h->corr_n != (size_t)si->n || si->n_seg != 1) return NGICP_OK;
+  if (!h->stream2) {
+    NGICP_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_spec, cudaEventDisableTiming));
+  }
+  NGICP_CUDA(h, cudaEventRecord(h->ev_main, h->stream));          // everything the search reads is ordered on the main stream
+  NGICP_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_main, 0));
+  const PoseArg P = make_pose(T);
+  launch_search(h, h->stream2, 1, P, nullptr, nullptr, h->k4_ball != 0, h->corr, h->corr_alt);
+  NGICP_CUDA(h, cudaGetLastError());
+  NGICP_CUDA(h, cudaEventRecord(h->ev_spec, h->stream2));
+  std::memcpy(h->spec_T, T, sizeof h->spec_T);
+  h->spec_pending = true;
+  return NGICP_OK;
+}
+
+// orders the main stream after any speculative search still in flight (before the index, the list or the buffers it
+// uses are touched again) and forgets it
+void drop_speculation(Handle* h) {
+  if (h->spec_pending) cudaStreamWaitEvent(h->stream, h->ev_spec, 0);
+  h->spec_pending = false;
 }
 
 static void unpack_result(const double* v, bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
@@ -602,7 +650,13 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
   if (int rc = ensure_corr(h, si->n)) return rc;
   const PoseArg P = make_pose(T);
   const unsigned long long seq = ++h->seq;
-  if (int rc = launch_linearize(h, 1, P, nullptr, nullptr, want_Hb, h->partials, seq)) return rc;
+  bool search_done = false;
+  if (h->spec_pending) {
+    search_done = h->lin_valid && h->corr_n == (size_t)si->n && std::memcmp(h->spec_T, T, sizeof h->spec_T) == 0;
+    drop_speculation(h);                                   // the main stream now follows the speculative search
+    if (search_done) std::swap(h->corr, h->corr_alt);
+  }
+  if (int rc = launch_linearize(h, 1, P, nullptr, nullptr, want_Hb, h->partials, seq, search_done)) return rc;
   int nc = 0;
   unpack_result(h->slot_host[0].v, want_Hb, H, b, err, &nc);
   h->num_correspondences = nc;
