@@ -67,6 +67,11 @@ __device__ __forceinline__ float bnn_cell_lb(int ix, int iy, int iz, float hL, f
   return (ex * ex + ey * ey + ez * ez) * 0.999999f;
 }
 
+// ceil(65536 / n) for the 1..5 cells a ball spans per axis: c / n == (c * r) >> 16 for c < 125, without an integer division
+__device__ __forceinline__ unsigned int bnn_recip16(int n) {
+  return n <= 1 ? 65536u : (n == 2 ? 32768u : (n == 3 ? 21846u : (n == 4 ? 16384u : 13108u)));
+}
+
 struct BallCells {
   int lox, loy, loz, nx, ny, nz, total;
 };
@@ -148,8 +153,7 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
   const BallCells bc = bnn_cells(ux, uy, uz, r, inv_hL, kMaxCoord >> base);
   if (bc.total > kBnnLightCells) { if (sub == 0) BNN_STAT(2, 1); return false; }
   // ---- batches of four probes per lane
-  const unsigned int rx = (65536u + (unsigned)max(bc.nx, 1) - 1u) / (unsigned)max(bc.nx, 1);   // c / nx == (c * rx) >> 16 for c < 125
-  const unsigned int ry = (65536u + (unsigned)max(bc.ny, 1) - 1u) / (unsigned)max(bc.ny, 1);
+  const unsigned int rx = bnn_recip16(bc.nx), ry = bnn_recip16(bc.ny);   // c / nx == (c * rx) >> 16 for c < 125
   const float slack = 2.0f * margin;
   constexpr int NB = 4;
   for (int cb = 0; cb < bc.total; cb += NB * LPQ) {          // uniform in the group
@@ -159,6 +163,10 @@ __device__ __forceinline__ bool bnn_group(const GridView& g, float qx, float qy,
   bool want[NB];
 #pragma unroll
   for (int t = 0; t < NB; t++) {
+    if (t >= 2 && bc.total <= cb + 2 * LPQ) {                  // the usual 2x2x2 ball: two cells per lane, skip the other two slots
+      want[t] = false; ck[t] = 0ull; hh[t] = 0u;
+      continue;
+    }
     const int c = cb + sub + LPQ * t;
     const int cyz = (int)(((unsigned)c * rx) >> 16);
     const int ox = c - cyz * bc.nx;
@@ -225,8 +233,7 @@ __device__ __forceinline__ bool bnn_warp(const GridView& g, float qx, float qy, 
   const float inv_hL = inv_h0 / (float)(1 << L);
   const BallCells bc = bnn_cells(ux, uy, uz, r, inv_hL, kMaxCoord >> L);
   if (bc.nx > kBnnSpan || bc.ny > kBnnSpan || bc.nz > kBnnSpan) return false;   // cannot happen; stay exact if it ever does
-  const unsigned int rx = (65536u + (unsigned)max(bc.nx, 1) - 1u) / (unsigned)max(bc.nx, 1);
-  const unsigned int ry = (65536u + (unsigned)max(bc.ny, 1) - 1u) / (unsigned)max(bc.ny, 1);
+  const unsigned int rx = bnn_recip16(bc.nx), ry = bnn_recip16(bc.ny);
   const float slack = 2.0f * margin;
   constexpr int NB = (kBnnSpan * kBnnSpan * kBnnSpan + 31) / 32;   // 4 probes per lane, all in flight
   unsigned long long ck[NB];
