@@ -5,17 +5,16 @@
 //   PLANE (default): JacobiSVD, C = U diag(1,1,1e-3) V^T                                   :365-385
 //   NONE / FROBENIUS / MIN_EIG / NORMALIZED_MIN_EIG                                        :356-363,375-381
 // For a symmetric PSD matrix U == V (distinct, positive singular values), so PLANE is
-// I - (1-1e-3) n n^T with n the eigenvector of the smallest eigenvalue; it is found in fp64 from the
-// trigonometric eigenvalue formula and the largest cross product of two rows of (A - lambda I).
+// I - (1-1e-3) n n^T with n the eigenvector of the smallest eigenvalue: n n^T = adj(A - lam I) / tr(adj), lam from
+// three fp64 Newton steps on the characteristic polynomial (eig3.cuh).
 // Ill-conditioned neighbourhoods (smallest two eigenvalues ~equal) fall back to cyclic Jacobi.
 // All arithmetic is fp64 from fp32 inputs, as in the reference; output is 6 x fp32 per point.
 #include "internal.h"
+#include "eig3.cuh"
 
 namespace ngicp {
 
 namespace {
-
-struct Sym3 { double xx, xy, xz, yy, yz, zz; };
 
 // cyclic Jacobi eigen-decomposition of a symmetric 3x3: A = V diag(w) V^T (columns of V)
 __device__ __noinline__ void jacobi_eig3(const Sym3& A, double w[3], double V[3][3]) {
@@ -49,57 +48,21 @@ __device__ __noinline__ void jacobi_eig3(const Sym3& A, double w[3], double V[3]
   w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
 }
 
-// unit eigenvector of the smallest eigenvalue of a symmetric PSD 3x3
-__device__ __forceinline__ void smallest_eigvec(const Sym3& A, double n[3]) {
-  const double scale = fmax(fmax(fabs(A.xx), fabs(A.yy)), fmax(fabs(A.zz), fmax(fabs(A.xy), fmax(fabs(A.xz), fabs(A.yz)))));
-  bool ok = scale > 0.0;
-  if (ok) {
-    const double inv = 1.0 / scale;
-    const double a00 = A.xx * inv, a01 = A.xy * inv, a02 = A.xz * inv, a11 = A.yy * inv, a12 = A.yz * inv, a22 = A.zz * inv;
-    const double q = (a00 + a11 + a22) * (1.0 / 3.0);
-    const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-    const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
-    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
-    const double p = sqrt(p2 * (1.0 / 6.0));
-    double lam = q;
-    if (p > 1e-300) {
-      const double ip = 1.0 / p;
-      const double c00 = b00 * ip, c01 = a01 * ip, c02 = a02 * ip, c11 = b11 * ip, c12 = a12 * ip, c22 = b22 * ip;
-      double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
-      r = fmin(1.0, fmax(-1.0, r));
-      const double phi = acos(r) * (1.0 / 3.0);
-      lam = q + 2.0 * p * cos(phi + 2.0943951023931954923);  // smallest root
-    }
-    // rows of (A - lam I); the eigenvector is orthogonal to all of them
-    const double r0x = a00 - lam, r0y = a01, r0z = a02;
-    const double r1x = a01, r1y = a11 - lam, r1z = a12;
-    const double r2x = a02, r2y = a12, r2z = a22 - lam;
-    const double c0x = r0y * r1z - r0z * r1y, c0y = r0z * r1x - r0x * r1z, c0z = r0x * r1y - r0y * r1x;
-    const double c1x = r0y * r2z - r0z * r2y, c1y = r0z * r2x - r0x * r2z, c1z = r0x * r2y - r0y * r2x;
-    const double c2x = r1y * r2z - r1z * r2y, c2y = r1z * r2x - r1x * r2z, c2z = r1x * r2y - r1y * r2x;
-    const double n0 = c0x * c0x + c0y * c0y + c0z * c0z;
-    const double n1 = c1x * c1x + c1y * c1y + c1z * c1z;
-    const double n2 = c2x * c2x + c2y * c2y + c2z * c2z;
-    double bx = c0x, by = c0y, bz = c0z, bn = n0;
-    if (n1 > bn) { bx = c1x; by = c1y; bz = c1z; bn = n1; }
-    if (n2 > bn) { bx = c2x; by = c2y; bz = c2z; bn = n2; }
-    // |cross| ~ (lam_mid - lam_min)(lam_max - lam_min) on the unit-scaled matrix; tiny => the two
-    // smallest eigenvalues (nearly) coincide and the direction is ill-defined: use Jacobi.
-    if (bn > 1e-16) {
-      const double rn = rsqrt(bn);
-      n[0] = bx * rn; n[1] = by * rn; n[2] = bz * rn;
-      return;
-    }
-  }
-  double w[3], V[3][3];
+// exact path of PLANE for the neighbourhoods plane_regularize_fast (eig3.cuh) refuses: unit eigenvector of the
+// smallest eigenvalue by cyclic Jacobi
+__device__ __noinline__ void plane_regularize_exact(const Sym3& A, Sym3& o) {
+  double w[3], V[3][3], n[3];
   jacobi_eig3(A, w, V);
   int m = 0;
   if (w[1] < w[m]) m = 1;
   if (w[2] < w[m]) m = 2;
-  if (!(w[0] == w[0])) { n[0] = 0; n[1] = 0; n[2] = 1; return; }
   // exact ties (e.g. the all-zero matrix): the reference's sorted SVD keeps the LAST column small
   if (w[0] == w[1] && w[1] == w[2]) m = 2;
   n[0] = V[0][m]; n[1] = V[1][m]; n[2] = V[2][m];
+  if (!(w[0] == w[0])) { n[0] = 0; n[1] = 0; n[2] = 1; }
+  const double f = 1.0 - 1e-3;
+  o.xx = 1.0 - f * n[0] * n[0]; o.xy = -f * n[0] * n[1]; o.xz = -f * n[0] * n[2];
+  o.yy = 1.0 - f * n[1] * n[1]; o.yz = -f * n[1] * n[2]; o.zz = 1.0 - f * n[2] * n[2];
 }
 
 __device__ __forceinline__ Sym3 inverse_sym3(const Sym3& a) {
@@ -120,12 +83,8 @@ template <int REG>
 __device__ __forceinline__ Sym3 regularize(const Sym3& cov) {
   if (REG == NGICP_REG_NONE) return cov;
   if (REG == NGICP_REG_PLANE) {
-    double n[3];
-    smallest_eigvec(cov, n);
-    const double f = 1.0 - 1e-3;
     Sym3 o;
-    o.xx = 1.0 - f * n[0] * n[0]; o.xy = -f * n[0] * n[1]; o.xz = -f * n[0] * n[2];
-    o.yy = 1.0 - f * n[1] * n[1]; o.yz = -f * n[1] * n[2]; o.zz = 1.0 - f * n[2] * n[2];
+    if (!plane_regularize_fast(cov, o)) plane_regularize_exact(cov, o);
     return o;
   }
   if (REG == NGICP_REG_FROBENIUS) {  // nano_gicp.cc:358-363
@@ -157,12 +116,22 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov) {
   return o;
 }
 
+// Exact fp32 -> fp64 widening on the integer pipe (shift, mask, re-bias: 4 instructions) for the coordinates the
+// conversion unit (F2F.F64.F32, a quarter-rate pipe shared with MUFU) would otherwise serialise. Zero and denormal
+// inputs come out as ~2^-127 instead of 0: below half an ulp of any difference this kernel forms.
+__device__ __forceinline__ double widen(float x) {
+  const unsigned b = __float_as_uint(x);
+  const unsigned hi = (((unsigned)((int)b >> 3)) & 0x8FFFFFFFu) + 0x38000000u;
+  return __hiloint2double((int)hi, (int)(b << 29));
+}
+template <int ICVT, int BIT>
+__device__ __forceinline__ double to_f64(float x) { return (ICVT & BIT) ? widen(x) : (double)x; }
+
 // K = compile-time k (vector index loads, fully unrolled gathers) or 0 for a runtime k.
-template <int K, int REG>
-__global__ void __launch_bounds__(128) covariance_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
-                                                         float* __restrict__ cov6) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// ICVT = bit mask of the neighbour coordinates (x=1, y=2, z=4) widened on the integer pipe.
+template <int K, int REG, int ICVT>
+__device__ __forceinline__ void covariance_point(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                 float* __restrict__ cov6, int j) {
   const int k = K > 0 ? K : k_rt;
   const float4 pj = __ldg(pts + j);
   const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
@@ -185,7 +154,7 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
       for (int i = 0; i < kBatch; i++) nb[i] = __ldg(pts + id[b0 + i]);
 #pragma unroll
       for (int i = 0; i < kBatch; i++) {
-        const double dx = (double)nb[i].x - ox, dy = (double)nb[i].y - oy, dz = (double)nb[i].z - oz;
+        const double dx = to_f64<ICVT, 1>(nb[i].x) - ox, dy = to_f64<ICVT, 2>(nb[i].y) - oy, dz = to_f64<ICVT, 4>(nb[i].z) - oz;
         sx += dx; sy += dy; sz += dz;
         sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
       }
@@ -208,6 +177,19 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
   out[0] = make_float2((float)o.xx, (float)o.xy);
   out[1] = make_float2((float)o.xz, (float)o.yy);
   out[2] = make_float2((float)o.yz, (float)o.zz);
+}
+
+template <int K, int REG>
+__global__ void __launch_bounds__(128) covariance_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                         float* __restrict__ cov6) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) covariance_point<K, REG, 0>(pts, nbr, n, k_rt, cov6, j);
+}
+template <int K, int REG, int ICVT>
+__global__ void __launch_bounds__(128, 7) covariance_kernel_i(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                              float* __restrict__ cov6) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) covariance_point<K, REG, ICVT>(pts, nbr, n, k_rt, cov6, j);
 }
 
 // ---- layout conversions between the host's CovarianceList order and the device's sorted order ----
@@ -259,9 +241,14 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
   const int nb = (n + 127) / 128;
   cudaStream_t s = h->stream;
 #define LAUNCH_COV(K, REG) covariance_kernel<K, REG><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
+#define LAUNCH_COV_I(K, REG, I) covariance_kernel_i<K, REG, I><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
+  static const int icvt = getenv("NGICP_K3_ICVT") ? atoi(getenv("NGICP_K3_ICVT")) : 0;  // development switch
 #define LAUNCH_COV_K(REG)            \
   do {                               \
-    if (k == 16) LAUNCH_COV(16, REG); \
+    if (k == 16 && REG == NGICP_REG_PLANE && icvt == 1) LAUNCH_COV_I(16, REG, 4); \
+    else if (k == 16 && REG == NGICP_REG_PLANE && icvt == 2) LAUNCH_COV_I(16, REG, 6); \
+    else if (k == 16 && REG == NGICP_REG_PLANE && icvt == 3) LAUNCH_COV_I(16, REG, 7); \
+    else if (k == 16) LAUNCH_COV(16, REG); \
     else if (k == 20) LAUNCH_COV(20, REG); \
     else LAUNCH_COV(0, REG);         \
   } while (0)
@@ -275,6 +262,7 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
   }
 #undef LAUNCH_COV_K
 #undef LAUNCH_COV
+#undef LAUNCH_COV_I
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;

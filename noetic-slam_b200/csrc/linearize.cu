@@ -291,7 +291,10 @@ __global__ void __launch_bounds__(kLinThreads, 5) correspond_heavy_kernel(GridVi
 // (C_B + R C_A R^T)^-1, the residual, the 6-DoF Jacobian and the 21 + 6 + 1 (+ count) contributions, accumulated in
 // fp64 registers, reduced by warp shuffles, per block, and by the last block to finish (fixed order, compensated).
 // A streaming kernel: 16 B p_A + 24 B C_A + 4 B corr + gathers of 16 B p_B + 24 B C_B per point, nothing written per point.
-template <bool WANT_HB>
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// PF: also pull the NEXT trip's gather targets (p_B, C_B; correspondence fetched two trips ahead) into L1
+template <bool WANT_HB, bool PF = false>
 __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, GridView tgt, const float* __restrict__ cov_src, const float* __restrict__ cov_tgt,
                                                                  PoseArg pose0, const PoseArg* __restrict__ poses, const int* __restrict__ corr,
                                                                  double* __restrict__ partials, unsigned int* __restrict__ counters,
@@ -304,8 +307,25 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(GridView src, Gr
   double acc[kTerms];
 #pragma unroll
   for (int t = 0; t < kTerms; t++) acc[t] = 0.0;
-  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
-    const int pos = __ldg(corr + j);
+  // the correspondence of the NEXT trip is fetched one trip ahead, so the dependent gathers (p_B, C_B) leave together
+  // with the streaming loads (p_A, C_A) instead of one memory latency behind them
+  const int stride = gridDim.x * kLinThreads;
+  int j = begin + blockIdx.x * kLinThreads + threadIdx.x;
+  int pos_next = j < end ? __ldg(corr + j) : -1;
+  int pos_next2 = (PF && j + stride < end) ? __ldg(corr + j + stride) : -1;
+  for (; j < end; j += stride) {
+    const int pos = pos_next;
+    if (PF) {
+      pos_next = pos_next2;
+      pos_next2 = j + 2 * stride < end ? __ldg(corr + j + 2 * stride) : -1;
+      if (pos_next >= 0) {
+        prefetch_l1(tgt.pts + pos_next);
+        prefetch_l1(cov_tgt + (size_t)pos_next * 6);
+        prefetch_l1(cov_tgt + (size_t)pos_next * 6 + 5);
+      }
+    } else {
+      pos_next = j + stride < end ? __ldg(corr + j + stride) : -1;
+    }
     if (pos < 0) continue;
     const float4 pa = __ldg(src.pts + j);
     const float4 pb = __ldg(tgt.pts + pos);
@@ -370,8 +390,12 @@ __global__ void __launch_bounds__(kLinThreads) error_kernel(GridView src, GridVi
   const int end = src.n_seg > 1 ? __ldg(src.seg_start + b + 1) : src.n;
   __shared__ double wsum[kLinThreads / 32][1];
   double acc[1] = {0.0};
-  for (int j = begin + blockIdx.x * kLinThreads + threadIdx.x; j < end; j += gridDim.x * kLinThreads) {
-    const int pos = __ldg(corr + j);
+  const int stride = gridDim.x * kLinThreads;
+  int j = begin + blockIdx.x * kLinThreads + threadIdx.x;
+  int pos_next = j < end ? __ldg(corr + j) : -1;   // one trip ahead, as in K4b
+  for (; j < end; j += stride) {
+    const int pos = pos_next;
+    pos_next = j + stride < end ? __ldg(corr + j + stride) : -1;
     if (pos < 0) continue;
     const float4 pa = __ldg(src.pts + j);
     const float4 pb = __ldg(tgt.pts + pos);
@@ -571,14 +595,19 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   const Index* si = h->index[0];
   const int per_scan = si->n / n_scans + 1;
   // batched: few fat blocks per scan (many points per thread amortise the 29-term block reduction); single scan: wide
-  const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * 8) / n_scans)), n_scans);
+  static const int lin_mult = getenv("NGICP_K4B_MULT") ? atoi(getenv("NGICP_K4B_MULT")) : 8;   // development switches
+  static const bool lin_pf = getenv("NGICP_K4B_PF") && atoi(getenv("NGICP_K4B_PF"));
+  const dim3 lgrid(std::max(1, std::min(lin_blocks_for(per_scan), (148 * lin_mult) / n_scans)), n_scans);
   // the correspondences of the previous linearize (same clouds) seed this one
   const bool use_prev = h->lin_valid && h->k4_ball && h->corr_n == (size_t)si->n;
   if (h->timing) cudaEventRecord(h->ev[0], h->stream);
   if (!search_done) launch_search(h, h->stream, n_scans, P0, d_poses, d_target_seg, use_prev, h->corr, h->corr);
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
   const Index* ti = h->index[1];
-  if (want_Hb)
+  if (want_Hb && lin_pf)
+    linearize_kernel<true, true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
+                                                                      h->counter, h->slot_dev, seq);
+  else if (want_Hb)
     linearize_kernel<true><<<lgrid, kLinThreads, 0, h->stream>>>(si->view(), ti->view(), h->covs[0].cov6, h->covs[1].cov6, P0, d_poses, h->corr, partials,
                                                                 h->counter, h->slot_dev, seq);
   else
