@@ -11,6 +11,7 @@
 // All arithmetic is fp64 from fp32 inputs, as in the reference; output is 6 x fp32 per point.
 #include "internal.h"
 #include "eig3.cuh"
+#include "tma.cuh"
 
 namespace ngicp {
 
@@ -116,59 +117,31 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov) {
   return o;
 }
 
-// Exact fp32 -> fp64 widening on the integer pipe (shift, mask, re-bias: 4 instructions) for the coordinates the
-// conversion unit (F2F.F64.F32, a quarter-rate pipe shared with MUFU) would otherwise serialise. Zero and denormal
-// inputs come out as ~2^-127 instead of 0: below half an ulp of any difference this kernel forms.
-__device__ __forceinline__ double widen(float x) {
-  const unsigned b = __float_as_uint(x);
-  const unsigned hi = (((unsigned)((int)b >> 3)) & 0x8FFFFFFFu) + 0x38000000u;
-  return __hiloint2double((int)hi, (int)(b << 29));
-}
-template <int ICVT, int BIT>
-__device__ __forceinline__ double to_f64(float x) { return (ICVT & BIT) ? widen(x) : (double)x; }
-
-// K = compile-time k (vector index loads, fully unrolled gathers) or 0 for a runtime k.
-// ICVT = bit mask of the neighbour coordinates (x=1, y=2, z=4) widened on the integer pipe.
-template <int K, int REG, int ICVT>
-__device__ __forceinline__ void covariance_point(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
-                                                 float* __restrict__ cov6, int j) {
-  const int k = K > 0 ? K : k_rt;
-  const float4 pj = __ldg(pts + j);
+// scatter matrix of the K gathered neighbours about the query point, covariance, regularisation, 24-byte store
+// (the rows come from global memory in the per-point kernel and from the TMA-staged tile in the streaming kernel)
+template <int K, int REG, typename Row4>
+__device__ __forceinline__ void covariance_from_ids(const float4* __restrict__ pts, const float4 pj, Row4 row4, float* __restrict__ cov6, int j) {
   const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
   double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-  const int* row = nbr + (size_t)j * k;
-  if (K > 0) {
-    int id[K > 0 ? K : 1];
+  // gathers in batches of kBatch: enough loads in flight per thread, few enough registers for 28 warps per SM
+  constexpr int kBatch = K % 8 == 0 ? 8 : 4;
 #pragma unroll
-    for (int i = 0; i < K; i += 4) {
-      const int4 v = __ldg(reinterpret_cast<const int4*>(row) + i / 4);
-      id[i] = v.x; id[i + 1] = v.y; id[i + 2] = v.z; id[i + 3] = v.w;
+  for (int b0 = 0; b0 < K; b0 += kBatch) {
+    float4 nb[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; i += 4) {
+      const int4 v = row4((b0 + i) / 4);
+      nb[i] = __ldg(pts + v.x); nb[i + 1] = __ldg(pts + v.y); nb[i + 2] = __ldg(pts + v.z); nb[i + 3] = __ldg(pts + v.w);
     }
-    // gathers in batches of kBatch: enough loads in flight per thread, few enough registers for ~40 warps per SM
-    // (the kernel is bound by the fp64 pipe and needs the occupancy to keep it fed)
-    constexpr int kBatch = (K > 0 && K % 8 == 0) ? 8 : 4;
 #pragma unroll
-    for (int b0 = 0; b0 < K; b0 += kBatch) {
-      float4 nb[kBatch];
-#pragma unroll
-      for (int i = 0; i < kBatch; i++) nb[i] = __ldg(pts + id[b0 + i]);
-#pragma unroll
-      for (int i = 0; i < kBatch; i++) {
-        const double dx = to_f64<ICVT, 1>(nb[i].x) - ox, dy = to_f64<ICVT, 2>(nb[i].y) - oy, dz = to_f64<ICVT, 4>(nb[i].z) - oz;
-        sx += dx; sy += dy; sz += dz;
-        sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
-      }
-    }
-  } else {
-    for (int i = 0; i < k; i++) {
-      const float4 p = __ldg(pts + __ldg(row + i));
-      const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
+    for (int i = 0; i < kBatch; i++) {
+      const double dx = (double)nb[i].x - ox, dy = (double)nb[i].y - oy, dz = (double)nb[i].z - oz;
       sx += dx; sy += dy; sz += dz;
       sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
     }
   }
   // cov = (S - s s^T / k) / k : covariance about the mean, divided by k (nano_gicp.cc:353-354)
-  const double ik = 1.0 / (double)k;
+  const double ik = 1.0 / (double)K;
   Sym3 c;
   c.xx = (sxx - sx * sx * ik) * ik; c.xy = (sxy - sx * sy * ik) * ik; c.xz = (sxz - sx * sz * ik) * ik;
   c.yy = (syy - sy * sy * ik) * ik; c.yz = (syz - sy * sz * ik) * ik; c.zz = (szz - sz * sz * ik) * ik;
@@ -179,17 +152,81 @@ __device__ __forceinline__ void covariance_point(const float4* __restrict__ pts,
   out[2] = make_float2((float)o.yz, (float)o.zz);
 }
 
+// One thread per point. K = compile-time k (vector index loads, fully unrolled gathers) or 0 for a runtime k.
 template <int K, int REG>
 __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
                                                          float* __restrict__ cov6) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) covariance_point<K, REG, 0>(pts, nbr, n, k_rt, cov6, j);
+  if (j >= n) return;
+  const float4 pj = __ldg(pts + j);
+  if constexpr (K > 0) {
+    const int4* row = reinterpret_cast<const int4*>(nbr + (size_t)j * K);
+    int4 id[K / 4];
+#pragma unroll
+    for (int i = 0; i < K / 4; i++) id[i] = __ldg(row + i);
+    covariance_from_ids<K, REG>(pts, pj, [&](int i) { return id[i]; }, cov6, j);
+  } else {
+    const int k = k_rt;
+    const int* row = nbr + (size_t)j * k;
+    const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    for (int i = 0; i < k; i++) {
+      const float4 p = __ldg(pts + __ldg(row + i));
+      const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
+      sx += dx; sy += dy; sz += dz;
+      sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
+    }
+    const double ik = 1.0 / (double)k;
+    Sym3 c;
+    c.xx = (sxx - sx * sx * ik) * ik; c.xy = (sxy - sx * sy * ik) * ik; c.xz = (sxz - sx * sz * ik) * ik;
+    c.yy = (syy - sy * sy * ik) * ik; c.yz = (syz - sy * sz * ik) * ik; c.zz = (szz - sz * sz * ik) * ik;
+    const Sym3 o = regularize<REG>(c);
+    float2* out = reinterpret_cast<float2*>(cov6 + (size_t)j * 6);
+    out[0] = make_float2((float)o.xx, (float)o.xy);
+    out[1] = make_float2((float)o.xz, (float)o.yy);
+    out[2] = make_float2((float)o.yz, (float)o.zz);
+  }
 }
-template <int K, int REG, int ICVT>
-__global__ void __launch_bounds__(128, 7) covariance_kernel_i(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
-                                                              float* __restrict__ cov6) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) covariance_point<K, REG, ICVT>(pts, nbr, n, k_rt, cov6, j);
+
+// Bulk builds (many keyframes in one launch): persistent warps, each streaming tiles of 32 points. The neighbour-index
+// rows of a tile are one contiguous run of 32 * K * 4 bytes: a single TMA bulk copy (cp.async.bulk, completing on the
+// warp's mbarrier) brings the NEXT tile's rows into shared memory while the warp works on the current one, so no warp
+// ever waits a DRAM round trip for its indices before it can issue its gathers. Double buffered per warp.
+constexpr int kCovWarps = 4;
+template <int K, int REG>
+__global__ void __launch_bounds__(kCovWarps * 32, 7) covariance_stream_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n,
+                                                                           float* __restrict__ cov6) {
+  __shared__ __align__(128) int rows[kCovWarps][2][32 * K];
+  __shared__ unsigned long long mbar[kCovWarps][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { mbar_init(&mbar[warp][0], 1); mbar_init(&mbar[warp][1], 1); }
+  __syncwarp();
+  const int n_tiles = (n + 31) >> 5;
+  const int stride = gridDim.x * kCovWarps;
+  int tile = blockIdx.x * kCovWarps + warp;
+  auto issue = [&](int t, int buf) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)min(32, n - t * 32) * (K * 4u);
+      mbar_expect_tx(&mbar[warp][buf], bytes);
+      tma_bulk_g2s(rows[warp][buf], nbr + (size_t)t * 32 * K, bytes, &mbar[warp][buf]);
+    }
+  };
+  if (tile < n_tiles) issue(tile, 0);
+  for (int it = 0; tile < n_tiles; tile += stride, it++) {
+    const int buf = it & 1;
+    const int j = tile * 32 + lane;
+    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n) pj = __ldg(pts + j);
+    // every lane finished reading the other buffer one trip ago (the __syncwarp at the end of the trip): refill it
+    if (tile + stride < n_tiles) issue(tile + stride, buf ^ 1);
+    while (!mbar_try_wait(&mbar[warp][buf], (it >> 1) & 1)) { }
+    if (j < n) {
+      const int4* row = reinterpret_cast<const int4*>(&rows[warp][buf][lane * K]);
+      covariance_from_ids<K, REG>(pts, pj, [&](int i) { return row[i]; }, cov6, j);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this buffer before the next async write
+    __syncwarp();
+  }
 }
 
 // ---- layout conversions between the host's CovarianceList order and the device's sorted order ----
@@ -241,13 +278,15 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
   const int nb = (n + 127) / 128;
   cudaStream_t s = h->stream;
 #define LAUNCH_COV(K, REG) covariance_kernel<K, REG><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
-#define LAUNCH_COV_I(K, REG, I) covariance_kernel_i<K, REG, I><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
-  static const int icvt = getenv("NGICP_K3_ICVT") ? atoi(getenv("NGICP_K3_ICVT")) : 0;  // development switch
+#define LAUNCH_STREAM(K, REG) covariance_stream_kernel<K, REG><<<stream_grid, kCovWarps * 32, 0, s>>>(idx->pts, d_nbr, n, d_cov6)
+  // bulk builds stream tiles through persistent warps (7 CTAs of 4 warps per SM at 72 registers); a single scan is one wave
+  static const int tma_switch = getenv("NGICP_K3_TMA") ? atoi(getenv("NGICP_K3_TMA")) : 1;   // development switch
+  const int stream_grid = 148 * 7;
+  const bool stream = tma_switch && (n + 31) / 32 >= 2 * stream_grid * kCovWarps;
 #define LAUNCH_COV_K(REG)            \
   do {                               \
-    if (k == 16 && REG == NGICP_REG_PLANE && icvt == 1) LAUNCH_COV_I(16, REG, 4); \
-    else if (k == 16 && REG == NGICP_REG_PLANE && icvt == 2) LAUNCH_COV_I(16, REG, 6); \
-    else if (k == 16 && REG == NGICP_REG_PLANE && icvt == 3) LAUNCH_COV_I(16, REG, 7); \
+    if (k == 16 && stream) LAUNCH_STREAM(16, REG); \
+    else if (k == 20 && stream) LAUNCH_STREAM(20, REG); \
     else if (k == 16) LAUNCH_COV(16, REG); \
     else if (k == 20) LAUNCH_COV(20, REG); \
     else LAUNCH_COV(0, REG);         \
@@ -260,9 +299,9 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
     case NGICP_REG_FROBENIUS: LAUNCH_COV(0, NGICP_REG_FROBENIUS); break;
     default: return fail(h, NGICP_ERR_INVALID, "unknown regularization method");  // reference aborts (nano_gicp.cc:369-371)
   }
+#undef LAUNCH_STREAM
 #undef LAUNCH_COV_K
 #undef LAUNCH_COV
-#undef LAUNCH_COV_I
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;

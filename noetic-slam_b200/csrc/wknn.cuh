@@ -18,6 +18,7 @@
 //      coarser group next time.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ngicp {
 
@@ -45,25 +46,6 @@ struct __align__(16) WarpScratch {
   float4 qm[8];                 // member queries of the current pass (k = 1 path)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* mbar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* mbar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// TMA 1-D bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
-}
 
 // Stage candidates [c0, c0+nch) of the concatenated bucket list into shared-memory buffer `buf`. Every voxel bucket
 // is a contiguous run of float4 in the Morton-sorted array, so each overlapping bucket is ONE TMA bulk copy

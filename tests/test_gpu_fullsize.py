@@ -73,3 +73,31 @@ def test_align_65k_vs_1m_matches_oracle_and_truth(big):
     # the optimum beats its neighbourhood under the cached-correspondence error
     e0, _, _ = g.linearize(T.astype(np.float64))
     assert e0 <= g.compute_error(synth.se3((0, 0, 0.002), (0.01, 0, 0)) @ T.astype(np.float64))
+
+
+def test_bulk_covariances_match_the_oracle(big):
+    """The bulk build (persistent warps, TMA-staged index rows) on 4 keyframes x 65,536 points against the oracle's
+    calculate_covariances per keyframe: 1e-4 relative on every row with a spectral gap (north star), and the per-point
+    kernel a single scan runs gives bit-identical rows."""
+    sc = synth.Scene(1)
+    rng = np.random.default_rng(11)
+    poses = synth.trajectory(sc, 5, 1, step=1.0)
+    clouds = [synth.transform_points(P, synth.scan(sc, P, rng, keep_all=True)) for P in poses]
+    pts = np.concatenate(clouds)
+    off = np.arange(len(clouds) + 1, dtype=np.int64) * 65536
+    g = S.configure(ngicp.NanoGICP(0))
+    cov6, m4, dens = g.batchCovariances(pts, off, want_mat4=True)
+    assert len(pts) >= 2 * 148 * 7 * 128                       # large enough for the streaming kernel (covariance.cu)
+    o = S.configure(oracle.OracleGICP("port"))
+    for i in (0, 4):
+        a = clouds[i]
+        o.setInputSource(a); o.calculateSourceCovariances()
+        Co = o.getSourceCovariances()
+        idx, _ = oracle.KdTree(a, "port").knn(a, 16)
+        ok = S.spectral_gap_ok(a, idx)
+        assert ok.mean() > 0.9
+        assert np.abs(m4[off[i]:off[i + 1]] - Co)[ok].max() < 1e-4
+        assert abs(dens[i] - o.source_density_) <= 1e-5 * abs(o.source_density_)
+        g1 = S.configure(ngicp.NanoGICP(0))
+        g1.setInputSource(a); g1.calculateSourceCovariances()
+        assert (g1.getSourceCovariances() == m4[off[i]:off[i + 1]]).all()

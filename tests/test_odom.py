@@ -1,0 +1,142 @@
+"""The odom-loop harness: host policy on CPU; the loop over the CUDA path against the same loop over
+the oracle on the GPU box."""
+import numpy as np
+import pytest
+
+from ngicp import odom, synth
+from odom_backends import FakeBackend
+
+
+def test_push_submap_indices_keeps_ties_and_k_smallest():
+    # pushSubmapIndices (reference src/dlio/src/dlio/odom.cc:1628-1652): <= k-th smallest, ties included
+    assert odom.push_submap_indices([3.0, 1.0, 2.0, 2.0, 5.0], 2, [10, 11, 12, 13, 14]) == [11, 12, 13]
+    assert odom.push_submap_indices([], 3, []) == []
+    assert odom.push_submap_indices([1.0, 2.0], 10, [7, 8]) == [7, 8]
+
+
+def test_convex_hull_planar_and_spatial():
+    sq = np.array([[0, 0, 0], [4, 0, 0], [4, 4, 0], [0, 4, 0], [2, 2, 0], [1, 3, 0]], float)
+    assert odom.convex_hull_indices(sq) == [0, 1, 2, 3]                       # coplanar keyframes: the 2-D hull
+    cube = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)] + [[0.5, 0.5, 0.5]], float)
+    assert odom.convex_hull_indices(cube) == list(range(8))
+    line = np.array([[i, 2 * i, 0.0] for i in range(6)])
+    assert odom.convex_hull_indices(line) == [0, 5]
+
+
+def test_concave_hull_follows_a_c_shaped_path():
+    ang = np.deg2rad(np.arange(0, 271, 10.0))
+    outer = np.stack([5 * np.cos(ang), 5 * np.sin(ang), 0 * ang], 1)
+    inner = np.stack([4 * np.cos(ang), 4 * np.sin(ang), 0 * ang], 1)
+    P = np.concatenate([outer, inner])
+    hull = odom.concave_hull_indices(P, alpha=1.0)
+    convex = odom.convex_hull_indices(P)
+    n = len(ang)
+    assert set(range(n, 2 * n)) <= set(hull)                                  # the inner arc is on the alpha shape ...
+    assert not (set(range(n + 2, 2 * n - 2)) & set(convex))                   # ... and not on the convex hull
+    assert set(range(n)) <= set(hull)
+    assert odom.concave_hull_indices(P, alpha=0.1) == []                      # alpha below every circumradius: nothing kept
+
+
+def test_quaternion_helpers():
+    R = synth.rot_from_rotvec([0.1, -0.2, 0.7])
+    q = odom.quat_from_rot(R)
+    assert abs(np.linalg.norm(q) - 1) < 1e-12
+    assert abs(odom.quat_angle_deg(q, q)) < 1e-6
+    r = odom.quat_from_rot(synth.rot_from_rotvec([0, 0, np.deg2rad(50.0)]))
+    assert abs(odom.quat_angle_deg(r, [1, 0, 0, 0]) - 50.0) < 1e-9
+    assert abs(odom.quat_angle_deg(r, [-1, 0, 0, 0]) - 50.0) < 1e-9           # sign fix (odom.cc:1560-1568)
+
+
+def _records(n=2000, seed=0):
+    rng = np.random.default_rng(seed)
+    rec = np.zeros(n, odom.OS1_RECORD)
+    xyz = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    rec["x"], rec["y"], rec["z"] = xyz.T
+    rec["t"] = rng.integers(0, 4, n)
+    return rec
+
+
+def test_keyframe_policy_and_submap_changes_with_a_scripted_backend():
+    """Straight drive, 0.4 m per scan, identity corrections: a keyframe whenever the closest one is farther than the
+    adaptive threshold (spaciousness clamps it into [0.5, 5]), every new keyframe transformed exactly once, the submap
+    re-assembled only when the keyframe set changes (odom.cc:1517-1598, 1700-1741)."""
+    n = 24
+    be = FakeBackend([np.eye(4, dtype=np.float32)] * n)
+    loop = odom.OdomLoop(be, odom.OdomParams(adaptive=True))
+    rec = _records()
+    pose = lambda i: synth.se3((0, 0, 0), (0.4 * i, 0, 0)).astype(np.float32)
+    out = [loop.callbackPointCloud(rec, None)]
+    for i in range(1, n):
+        out.append(loop.callbackPointCloud(rec, lambda st, i=i: np.repeat(pose(i)[None], len(st), 0)))
+    thr = loop.keyframe_thresh_dist_
+    assert 0.5 <= thr <= 5.0
+    kf_x = np.array([k[0][0] for k in loop.keyframes])
+    assert len(kf_x) == be.captured and len(kf_x) >= 2
+    assert (np.diff(kf_x) > thr - 1e-6).all()                                 # never closer than the threshold
+    assert (np.diff(kf_x) <= thr + 0.4 + 1e-6).all()                          # and added as soon as it is exceeded
+    assert sorted(be.transformed) == list(range(be.captured))                 # each keyframe transformed once
+    assert be.max_corr and all(abs(d - 0.25) < 1e-12 for d in be.max_corr)    # adaptive: 0.5 * 0.5 (odom.cc:1616)
+    changes = sum(r.new_keyframe for r in out)
+    assert len(be.submaps) == changes                                          # one assembly per change of the set
+    assert be.submaps[-1] == sorted(set(be.submaps[-1]))
+    assert out[5].T[0, 3] == pytest.approx(0.4 * 5)
+
+
+def test_rotation_only_keyframe_needs_no_neighbours():
+    """abs(dd) <= threshD and theta > threshR only makes a keyframe when at most one keyframe is nearby (odom.cc:1586-1588)."""
+    be = FakeBackend([np.eye(4, dtype=np.float32)] * 4)
+    loop = odom.OdomLoop(be, odom.OdomParams(adaptive=False))
+    rec = _records()
+    loop.callbackPointCloud(rec, None)
+    turn = synth.se3((0, 0, np.deg2rad(60.0)), (0, 0, 0)).astype(np.float32)
+    r = loop.callbackPointCloud(rec, lambda st: np.repeat(turn[None], len(st), 0))
+    assert r.new_keyframe and len(loop.keyframes) == 2
+    turn2 = synth.se3((0, 0, np.deg2rad(120.0)), (0, 0, 0)).astype(np.float32)
+    r = loop.callbackPointCloud(rec, lambda st: np.repeat(turn2[None], len(st), 0))
+    assert not r.new_keyframe                                                 # two keyframes nearby now
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [odom.OdomParams(), odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5)], ids=["adaptive", "dense-keyframes"])
+def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params):
+    """BASELINE config 4 in miniature: the same seeded OS1-64 sequence (sensor moving during every scan, deskewed with
+    per-stamp priors, voxel filtered, keyframes and submap rebuilt) through the loop over the CUDA path and through the
+    loop over the CPU oracle: same keyframes, same submap sets, same iteration counts, poses within 1e-4 m / 1e-5 rad."""
+    import ngicp, oracle
+    import scenarios as S
+    from odom_backends import OracleBackend
+    scene = synth.Scene(3)
+    n, w, groups = 14, 256, 8
+    seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups))
+    rng = np.random.default_rng(5)
+    drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
+
+    def run(backend):
+        loop = odom.OdomLoop(backend, params)
+        res = []
+        for i, (rec, Ts, block, col_t) in enumerate(seq):
+            if i == 0:
+                loop.T = Ts[groups // 2].astype(np.float32)
+                loop.propagateGICP()
+                res.append(loop.callbackPointCloud(rec, None))
+                continue
+            # the prior the IMU integration would deliver: true motion inside the scan, a small seeded drift on top
+            def prior(stamps, Ts=Ts, i=i):
+                g = np.minimum((stamps.astype(np.int64) * groups) // 100_000_000, groups - 1)
+                return np.stack([(drift[i] @ Ts[k]).astype(np.float32) for k in g])
+            res.append(loop.callbackPointCloud(rec, prior))
+        return loop, res
+
+    g = S.configure(ngicp.NanoGICP(0), max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)
+    o = S.configure(oracle.OracleGICP("port"), max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)
+    lg, rg = run(odom.DeviceBackend(g))
+    lo, ro = run(OracleBackend(o))
+    assert len(lg.keyframes) == len(lo.keyframes) >= 2
+    for a, b in zip(rg, ro):
+        assert a.n_points == b.n_points and a.new_keyframe == b.new_keyframe and a.submap == b.submap
+        assert a.iterations == b.iterations and a.converged == b.converged
+        assert np.abs(a.T[:3, 3] - b.T[:3, 3]).max() < 1e-4
+        assert np.abs(a.T[:3, :3] - b.T[:3, :3]).max() < 1e-5
+    # and the loop tracks the truth: the drift of the prior is removed by the registration
+    err = [np.abs(r.T[:3, 3] - s[1][groups // 2][:3, 3]).max() for r, s in zip(rg[1:], seq[1:])]
+    assert max(err) < 0.1    # the first keyframe is not deskewed (no motion assumed, odom.cc:656-664): a few cm of map bias
