@@ -138,7 +138,7 @@ int compute_covariances_impl(Handle* h, int which, float* density) {
   c.cov6 = nullptr; c.valid = false; c.pending.clear(); c.pending_n = 0;
   int* d_nbr = nullptr; double* d_dens = nullptr; double* d_sum = nullptr;
   NGICP_CUDA(h, dev_alloc(&c.cov6, n * 6, s));
-  NGICP_CUDA(h, dev_alloc(&d_nbr, n * (size_t)k, s));
+  NGICP_CUDA(h, dev_alloc(&d_nbr, nbr_elems(n, k), s));
   NGICP_CUDA(h, dev_alloc(&d_dens, n, s));
   NGICP_CUDA(h, dev_alloc(&d_sum, (size_t)idx->n_seg, s));
   int rc;
@@ -716,7 +716,7 @@ int ngicp_batch_covariances(ngicp_handle* p, const void* points, size_t n, size_
   dev_free(d_xyz, st);
   if (rc) return rc;
   int* d_nbr = nullptr; double* d_dens = nullptr; double* d_sum = nullptr; float* d_cov = nullptr;
-  NGICP_CUDA(h, dev_alloc(&d_nbr, n * (size_t)k, st));
+  NGICP_CUDA(h, dev_alloc(&d_nbr, nbr_elems(n, k), st));
   NGICP_CUDA(h, dev_alloc(&d_dens, n, st));
   NGICP_CUDA(h, dev_alloc(&d_sum, (size_t)n_seg, st));
   NGICP_CUDA(h, dev_alloc(&d_cov, n * 6, st));

@@ -11,7 +11,6 @@
 // All arithmetic is fp64 from fp32 inputs, as in the reference; output is 6 x fp32 per point.
 #include "internal.h"
 #include "eig3.cuh"
-#include "tma.cuh"
 
 namespace ngicp {
 
@@ -117,24 +116,28 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov) {
   return o;
 }
 
-// scatter matrix of the K gathered neighbours about the query point, covariance, regularisation, 24-byte store
-// (the rows come from global memory in the per-point kernel and from the TMA-staged tile in the streaming kernel)
+// scatter matrix of the K gathered neighbours about the query point, covariance, regularisation, 24-byte store.
+// Neighbour 0 is the query itself (or an exact duplicate of it, distance 0): its difference is exactly zero, so it is
+// neither gathered nor accumulated — it only counts in the divisor k.
 template <int K, int REG, typename Row4>
 __device__ __forceinline__ void covariance_from_ids(const float4* __restrict__ pts, const float4 pj, Row4 row4, float* __restrict__ cov6, int j) {
   const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
   double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-  // gathers in batches of kBatch: enough loads in flight per thread, few enough registers for 28 warps per SM
-  constexpr int kBatch = K % 8 == 0 ? 8 : 4;
+  // gathers in batches of 8: enough loads in flight per thread, few enough registers for 28 warps per SM
+  int id[K];
 #pragma unroll
-  for (int b0 = 0; b0 < K; b0 += kBatch) {
-    float4 nb[kBatch];
+  for (int i = 0; i < K; i += 4) {
+    const int4 v = row4(i / 4);
+    id[i] = v.x; id[i + 1] = v.y; id[i + 2] = v.z; id[i + 3] = v.w;
+  }
 #pragma unroll
-    for (int i = 0; i < kBatch; i += 4) {
-      const int4 v = row4((b0 + i) / 4);
-      nb[i] = __ldg(pts + v.x); nb[i + 1] = __ldg(pts + v.y); nb[i + 2] = __ldg(pts + v.z); nb[i + 3] = __ldg(pts + v.w);
-    }
+  for (int b0 = 1; b0 < K; b0 += 8) {
+    constexpr int kB = 8;
+    float4 nb[kB];
 #pragma unroll
-    for (int i = 0; i < kBatch; i++) {
+    for (int i = 0; i < kB; i++) if (b0 + i < K) nb[i] = __ldg(pts + id[b0 + i]);
+#pragma unroll
+    for (int i = 0; i < kB; i++) if (b0 + i < K) {
       const double dx = (double)nb[i].x - ox, dy = (double)nb[i].y - oy, dz = (double)nb[i].z - oz;
       sx += dx; sy += dy; sz += dz;
       sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
@@ -160,17 +163,16 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
   if (j >= n) return;
   const float4 pj = __ldg(pts + j);
   if constexpr (K > 0) {
-    const int4* row = reinterpret_cast<const int4*>(nbr + (size_t)j * K);
-    int4 id[K / 4];
-#pragma unroll
-    for (int i = 0; i < K / 4; i++) id[i] = __ldg(row + i);
-    covariance_from_ids<K, REG>(pts, pj, [&](int i) { return id[i]; }, cov6, j);
+    // tiled k-NN table (internal.h:nbr_tiled): chunk c of the 32 points of a tile is contiguous, so a warp reads 512
+    // contiguous bytes per load (4 L1 wavefronts instead of the 16 of a 64-byte-strided row read)
+    const int4* tile = reinterpret_cast<const int4*>(nbr) + (size_t)(j >> 5) * (K / 4) * 32 + (j & 31);
+    covariance_from_ids<K, REG>(pts, pj, [&](int c) { return __ldg(tile + c * 32); }, cov6, j);
   } else {
     const int k = k_rt;
     const int* row = nbr + (size_t)j * k;
     const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    for (int i = 0; i < k; i++) {
+    for (int i = 1; i < k; i++) {     // neighbour 0 is the query itself: zero difference
       const float4 p = __ldg(pts + __ldg(row + i));
       const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
       sx += dx; sy += dy; sz += dz;
@@ -185,47 +187,6 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
     out[0] = make_float2((float)o.xx, (float)o.xy);
     out[1] = make_float2((float)o.xz, (float)o.yy);
     out[2] = make_float2((float)o.yz, (float)o.zz);
-  }
-}
-
-// Bulk builds (many keyframes in one launch): persistent warps, each streaming tiles of 32 points. The neighbour-index
-// rows of a tile are one contiguous run of 32 * K * 4 bytes: a single TMA bulk copy (cp.async.bulk, completing on the
-// warp's mbarrier) brings the NEXT tile's rows into shared memory while the warp works on the current one, so no warp
-// ever waits a DRAM round trip for its indices before it can issue its gathers. Double buffered per warp.
-constexpr int kCovWarps = 4;
-template <int K, int REG>
-__global__ void __launch_bounds__(kCovWarps * 32, 7) covariance_stream_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n,
-                                                                           float* __restrict__ cov6) {
-  __shared__ __align__(128) int rows[kCovWarps][2][32 * K];
-  __shared__ unsigned long long mbar[kCovWarps][2];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { mbar_init(&mbar[warp][0], 1); mbar_init(&mbar[warp][1], 1); }
-  __syncwarp();
-  const int n_tiles = (n + 31) >> 5;
-  const int stride = gridDim.x * kCovWarps;
-  int tile = blockIdx.x * kCovWarps + warp;
-  auto issue = [&](int t, int buf) {
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)min(32, n - t * 32) * (K * 4u);
-      mbar_expect_tx(&mbar[warp][buf], bytes);
-      tma_bulk_g2s(rows[warp][buf], nbr + (size_t)t * 32 * K, bytes, &mbar[warp][buf]);
-    }
-  };
-  if (tile < n_tiles) issue(tile, 0);
-  for (int it = 0; tile < n_tiles; tile += stride, it++) {
-    const int buf = it & 1;
-    const int j = tile * 32 + lane;
-    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < n) pj = __ldg(pts + j);
-    // every lane finished reading the other buffer one trip ago (the __syncwarp at the end of the trip): refill it
-    if (tile + stride < n_tiles) issue(tile + stride, buf ^ 1);
-    while (!mbar_try_wait(&mbar[warp][buf], (it >> 1) & 1)) { }
-    if (j < n) {
-      const int4* row = reinterpret_cast<const int4*>(&rows[warp][buf][lane * K]);
-      covariance_from_ids<K, REG>(pts, pj, [&](int i) { return row[i]; }, cov6, j);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this buffer before the next async write
-    __syncwarp();
   }
 }
 
@@ -278,16 +239,9 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
   const int nb = (n + 127) / 128;
   cudaStream_t s = h->stream;
 #define LAUNCH_COV(K, REG) covariance_kernel<K, REG><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
-#define LAUNCH_STREAM(K, REG) covariance_stream_kernel<K, REG><<<stream_grid, kCovWarps * 32, 0, s>>>(idx->pts, d_nbr, n, d_cov6)
-  // bulk builds stream tiles through persistent warps (7 CTAs of 4 warps per SM at 72 registers); a single scan is one wave
-  static const int tma_switch = getenv("NGICP_K3_TMA") ? atoi(getenv("NGICP_K3_TMA")) : 1;   // development switch
-  const int stream_grid = 148 * 7;
-  const bool stream = tma_switch && (n + 31) / 32 >= 2 * stream_grid * kCovWarps;
 #define LAUNCH_COV_K(REG)            \
   do {                               \
-    if (k == 16 && stream) LAUNCH_STREAM(16, REG); \
-    else if (k == 20 && stream) LAUNCH_STREAM(20, REG); \
-    else if (k == 16) LAUNCH_COV(16, REG); \
+    if (k == 16) LAUNCH_COV(16, REG); \
     else if (k == 20) LAUNCH_COV(20, REG); \
     else LAUNCH_COV(0, REG);         \
   } while (0)
@@ -299,7 +253,6 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
     case NGICP_REG_FROBENIUS: LAUNCH_COV(0, NGICP_REG_FROBENIUS); break;
     default: return fail(h, NGICP_ERR_INVALID, "unknown regularization method");  // reference aborts (nano_gicp.cc:369-371)
   }
-#undef LAUNCH_STREAM
 #undef LAUNCH_COV_K
 #undef LAUNCH_COV
   count_launch(h);

@@ -123,7 +123,12 @@ int fail(Handle* h, int code, const std::string& msg);
 // K1. xyz: device array of n points, `stride_floats` (3 or 4) floats apart.
 int build_index(Handle* h, const float* d_xyz, int stride_floats, int n, const int64_t* seg_offsets, int n_seg, Index** out);
 void free_index(Index* idx, cudaStream_t stream);
-// K2. self k-NN of every indexed point; nbr[n][k] = sorted positions (row = sorted position).
+// K2. self k-NN of every indexed point, as sorted positions. Layout of the table (transient between K2 and K3):
+// k = 16 / 20 (the compile-time paths of K3): TILED — points in tiles of 32, chunk c (int4 = neighbours 4c..4c+3) of
+// the 32 points of a tile contiguous: int4 index ((j / 32) * (k / 4) + c) * 32 + j % 32, so that both K2's writes and
+// K3's reads are contiguous across a warp; allocate nbr_elems(n, k) ints. Any other k: row-major nbr[n][k].
+inline bool nbr_tiled(int k) { return k == 16 || k == 20; }
+inline size_t nbr_elems(size_t n, int k) { return ((n + 31) / 32) * 32 * (size_t)k; }
 // dens_term[n] (optional) = sum_{j>=1} d2_j / normalization, the per-point density term.
 int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term);
 // public k-NN: queries on device (float4), results in ORIGINAL indices, canonical order

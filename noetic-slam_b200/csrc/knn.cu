@@ -15,6 +15,13 @@ namespace {
 // original index -> sorted position (what K3 gathers with); -1 stays -1
 __device__ __forceinline__ int topos(const GridView& g, int orig) { return orig >= 0 ? __ldg(g.inv + orig) : -1; }
 
+// where chunk c (neighbours 4c..4c+3) of point j goes: tiled for the k K3 reads with compile-time loops (internal.h)
+template <int K>
+__device__ __forceinline__ int4* nbr_chunk(int* __restrict__ nbr, int j, int c, bool tiled) {
+  return tiled ? reinterpret_cast<int4*>(nbr) + ((size_t)(j >> 5) * (K / 4) + c) * 32 + (j & 31)
+               : reinterpret_cast<int4*>(nbr + (size_t)j * K) + c;
+}
+
 template <class TK>
 __device__ __forceinline__ void self_query(const GridView& g, int j, int k, int start_count, int normalization,
                                            int* __restrict__ nbr, double* __restrict__ dens_term, TK& best) {
@@ -24,7 +31,7 @@ __device__ __forceinline__ void self_query(const GridView& g, int j, int k, int 
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int start_count, int normalization,
+__global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int start_count, int normalization, bool tiled,
                                                        int* __restrict__ nbr, double* __restrict__ dens_term) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= g.n) return;
@@ -34,7 +41,7 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
   if (k == K && (K % 4) == 0) {
 #pragma unroll
     for (int i = 0; i < K; i += 4)
-      reinterpret_cast<int4*>(row)[i / 4] = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
+      *nbr_chunk<K>(nbr, j, i / 4, tiled) = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
   } else {
 #pragma unroll
     for (int i = 0; i < K; i++) if (i < k) row[i] = topos(g, best.p[i]);
@@ -52,7 +59,7 @@ __global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int st
 // candidates (wknn.cuh).
 constexpr int kSelfWarps = 1;
 template <int K, int LPQ>
-__global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int cmax, int normalization,
+__global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int cmax, int normalization, bool tiled,
                                                                         int* __restrict__ nbr, double* __restrict__ dens_term) {
   __shared__ WarpScratch scratch[kSelfWarps];
   const int j = blockIdx.x * (blockDim.x / LPQ) + threadIdx.x / LPQ;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
   if (k == K && (K % 4) == 0) {
 #pragma unroll
     for (int i = 0; i < K; i += 4)
-      reinterpret_cast<int4*>(row)[i / 4] = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
+      *nbr_chunk<K>(nbr, j, i / 4, tiled) = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
   } else {
 #pragma unroll
     for (int i = 0; i < K; i++) if (i < k) row[i] = topos(g, best.p[i]);
@@ -160,7 +167,7 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   const int lpq = h->k2_lpq > 0 ? h->k2_lpq : (n < 1500000 ? 4 : 1);
 #define LAUNCH_SELF_L(K, LPQ)                                                                                             \
   knn_self_warp_kernel<K, LPQ><<<(n + (32 * kSelfWarps / LPQ) - 1) / (32 * kSelfWarps / LPQ), 32 * kSelfWarps, 0, s>>>( \
-      g, k, group_cap_for(k, h->k2_cmax_mult), normalization, d_nbr, d_dens_term)
+      g, k, group_cap_for(k, h->k2_cmax_mult), normalization, nbr_tiled(k), d_nbr, d_dens_term)
 #define LAUNCH_SELF(K) do { if (lpq >= 4) LAUNCH_SELF_L(K, 4); else LAUNCH_SELF_L(K, 1); } while (0)
   if (k == 1) LAUNCH_SELF(1);
   else if (k <= 8) LAUNCH_SELF(8);
