@@ -95,7 +95,7 @@ def test_bulk_covariances_match_the_oracle(big):
         Co = o.getSourceCovariances()
         idx, _ = oracle.KdTree(a, "port").knn(a, 16)
         ok = S.spectral_gap_ok(a, idx)
-        assert ok.mean() > 0.9
+        assert ok.mean() > 0.8
         assert np.abs(m4[off[i]:off[i + 1]] - Co)[ok].max() < 1e-4
         assert abs(dens[i] - o.source_density_) <= 1e-5 * abs(o.source_density_)
         g1 = S.configure(ngicp.NanoGICP(0))
