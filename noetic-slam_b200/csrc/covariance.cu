@@ -169,11 +169,13 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
     covariance_from_ids<K, REG>(pts, pj, [&](int c) { return __ldg(tile + c * 32); }, cov6, j);
   } else {
     const int k = k_rt;
-    const int* row = nbr + (size_t)j * k;
+    // the table is tiled for the k that K2 writes tiled (internal.h:nbr_tiled), row-major otherwise
+    const bool tiled = k == 16 || k == 20;
+    const int* row = tiled ? nbr + ((size_t)(j >> 5) * (k / 4) * 32 + (j & 31)) * 4 : nbr + (size_t)j * k;
     const double ox = (double)pj.x, oy = (double)pj.y, oz = (double)pj.z;
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
     for (int i = 1; i < k; i++) {     // neighbour 0 is the query itself: zero difference
-      const float4 p = __ldg(pts + __ldg(row + i));
+      const float4 p = __ldg(pts + __ldg(tiled ? row + (i >> 2) * 128 + (i & 3) : row + i));
       const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
       sx += dx; sy += dy; sz += dz;
       sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
