@@ -141,8 +141,9 @@ int compute_covariances_impl(Handle* h, int which, float* density) {
   NGICP_CUDA(h, dev_alloc(&d_nbr, nbr_elems(n, k), s));
   NGICP_CUDA(h, dev_alloc(&d_dens, n, s));
   NGICP_CUDA(h, dev_alloc(&d_sum, (size_t)idx->n_seg, s));
-  int rc;
-  {
+  int rc = NGICP_OK;
+  if (which == NGICP_SOURCE) rc = speculate_first_search(h);   // runs beside K2 + K3 on the second stream
+  if (!rc) {
     StageTimer t(h, &h->t.knn_ms);
     rc = knn_self(h, idx, k, d_nbr, d_dens);
   }
@@ -288,6 +289,7 @@ int ngicp_set_params(ngicp_handle* p, const ngicp_params* prm) {
   if (!p || !prm) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_params: NULL argument");
   if (prm->k_correspondences < 1) return fail(H(p), NGICP_ERR_INVALID, "k_correspondences must be >= 1");
   if (prm->regularization < 0 || prm->regularization > NGICP_REG_FROBENIUS) return fail(H(p), NGICP_ERR_INVALID, "unknown regularization method");
+  drop_speculation(H(p));   // a search in flight used the old gate
   H(p)->params = *prm;
   return NGICP_OK;
 }
@@ -411,6 +413,7 @@ int ngicp_attach_index(ngicp_handle* p, int which, ngicp_index* idx) {
   if (idx && idx->device != h->device) return fail(h, NGICP_ERR_INVALID, "index lives on another device");
   Index* old = h->index[which];
   if (old == idx) return NGICP_OK;
+  drop_speculation(h);
   NGICP_CUDA(h, cudaStreamSynchronize(h->stream));  // our pending work may still read the old index
   CovSet& c = h->covs[which];
   if (c.valid) {
@@ -493,6 +496,7 @@ int ngicp_set_input_device(ngicp_handle* p, int which, const void* d_points_f4, 
 int ngicp_swap_source_and_target(ngicp_handle* p) {
   if (!p) return NGICP_ERR_INVALID;
   Handle* h = H(p);
+  drop_speculation(h);
   std::swap(h->index[0], h->index[1]);
   std::swap(h->covs[0], h->covs[1]);
   h->lin_valid = false;  // correspondences_.clear(), nano_gicp.cc:102-103
@@ -503,6 +507,7 @@ int ngicp_clear(ngicp_handle* p, int which) {
   if (!p || (which != 0 && which != 1)) return NGICP_ERR_INVALID;
   Handle* h = H(p);
   if (int rc = use_device(h)) return rc;
+  drop_speculation(h);
   NGICP_CUDA(h, cudaStreamSynchronize(h->stream));
   release_index(h, h->index[which]);
   h->index[which] = nullptr;

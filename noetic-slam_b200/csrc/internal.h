@@ -64,6 +64,7 @@ struct ngicp_handle {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_main = nullptr, ev_spec = nullptr;
   bool spec_pending = false;
+  bool spec_first = false;      // the pending search is the first one of an align (no hints, no previous linearize)
   double spec_T[16];
   int k4_spec = 1;              // NGICP_K4_SPEC=0 disables
   void* heavy = nullptr;        // [corr_cap] HeavyQuery (linearize.cu): the queries the fast search kernel deferred
@@ -149,6 +150,7 @@ int compute_error_device(Handle* h, const double T[16], double* err);
 int batch_linearize_device(Handle* h, int n_scans, const double* T16s, double* H36s, double* b6s, double* errs, int* ncorrs);
 int export_correspondences(Handle* h, const double T[16], int32_t* corr, float* sqd, double* mahal, int* ncorr);
 int speculate_search(Handle* h, const double T[16]);
+int speculate_first_search(Handle* h);
 void drop_speculation(Handle* h);
 int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats, int n, const float T[16], float* d_xyz_out);
 

@@ -630,6 +630,14 @@ static int launch_linearize(Handle* h, int n_scans, const PoseArg& P0, const Pos
   return NGICP_OK;
 }
 
+// the second stream outranks the main one: a speculative search shares the GPU with K2 (8,192 blocks) or K5 and must get
+// its blocks resident as soon as slots free up, or it would simply queue behind them
+static cudaError_t create_search_stream(Handle* h) {
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  return cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, greatest);
+}
+
 // While K5 evaluates a trial pose on the main stream, search the correspondences AT that pose on a second stream: if
 // the LM step is accepted (the usual case) the next linearize starts with its search already done. Hints come from the
 // current correspondences (read-only here and in K5), results go to the alternate buffer; nothing is consumed unless
@@ -638,7 +646,7 @@ int speculate_search(Handle* h, const double T[16]) {
   const Index* si = h->index[0];
   if (!h->k4_spec || h->timing || !h->lin_valid || !h->corr_alt || h->corr_n != (size_t)si->n || si->n_seg != 1) return NGICP_OK;
   if (!h->stream2) {
-    NGICP_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    NGICP_CUDA(h, create_search_stream(h));
     NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_spec, cudaEventDisableTiming));
   }
@@ -653,11 +661,40 @@ int speculate_search(Handle* h, const double T[16]) {
   return NGICP_OK;
 }
 
+// The FIRST search of the coming align does not need the source covariances: started from calculate*Covariances for the
+// source (api.cu:compute_covariances_impl) on the second stream, it runs beside K2 + K3. The pose is the identity — DLIO
+// hands GICP scans that are already in the world frame and aligns without a guess (reference src/dlio/src/dlio/odom.cc:1005);
+// any other first pose, a changed target / source / parameter set in between simply discards the result.
+int speculate_first_search(Handle* h) {
+  const Index* si = h->index[0];
+  const Index* ti = h->index[1];
+  if (!h->k4_spec || h->timing || !si || !ti || si->n_seg != 1 || ti->n_seg != 1) return NGICP_OK;
+  if (int rc = ensure_corr(h, si->n)) return rc;
+  drop_speculation(h);
+  if (!h->stream2) {
+    NGICP_CUDA(h, create_search_stream(h));
+    NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    NGICP_CUDA(h, cudaEventCreateWithFlags(&h->ev_spec, cudaEventDisableTiming));
+  }
+  NGICP_CUDA(h, cudaEventRecord(h->ev_main, h->stream));          // the source index build is ordered on the main stream
+  NGICP_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_main, 0));
+  double T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const PoseArg P = make_pose(T);
+  launch_search(h, h->stream2, 1, P, nullptr, nullptr, false, h->corr, h->corr_alt);
+  NGICP_CUDA(h, cudaGetLastError());
+  NGICP_CUDA(h, cudaEventRecord(h->ev_spec, h->stream2));
+  std::memcpy(h->spec_T, T, sizeof h->spec_T);
+  h->spec_pending = true;
+  h->spec_first = true;
+  return NGICP_OK;
+}
+
 // orders the main stream after any speculative search still in flight (before the index, the list or the buffers it
 // uses are touched again) and forgets it
 void drop_speculation(Handle* h) {
   if (h->spec_pending) cudaStreamWaitEvent(h->stream, h->ev_spec, 0);
   h->spec_pending = false;
+  h->spec_first = false;
 }
 
 static void unpack_result(const double* v, bool want_Hb, double H[36], double b[6], double* err, int* ncorr) {
@@ -681,7 +718,7 @@ int linearize_device(Handle* h, const double T[16], bool want_Hb, double H[36], 
   const unsigned long long seq = ++h->seq;
   bool search_done = false;
   if (h->spec_pending) {
-    search_done = h->lin_valid && h->corr_n == (size_t)si->n && std::memcmp(h->spec_T, T, sizeof h->spec_T) == 0;
+    search_done = (h->spec_first || (h->lin_valid && h->corr_n == (size_t)si->n)) && std::memcmp(h->spec_T, T, sizeof h->spec_T) == 0;
     drop_speculation(h);                                   // the main stream now follows the speculative search
     if (search_done) std::swap(h->corr, h->corr_alt);
   }
