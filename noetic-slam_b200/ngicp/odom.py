@@ -214,8 +214,8 @@ class OdomLoop:
         self.concave_alpha = self.p.keyframe_thresh_dist
 
     # ---- metrics and adaptive parameters (odom.cc:1398-1436, 1600-1626) ----
-    def computeSpaciousness(self, xyz):
-        d = np.sqrt(xyz[:, 0].astype(np.float32) ** 2 + xyz[:, 1].astype(np.float32) ** 2)
+    def computeSpaciousness(self, x, y):
+        d = np.sqrt(x * x + y * y)
         median_curr = float(np.partition(d, len(d) // 2)[len(d) // 2])
         if self._median_prev is None:
             self._median_prev = median_curr
@@ -261,9 +261,11 @@ class OdomLoop:
         n_src, self.source_density_ = self.b.deskew_filter_set_source(frames, p.voxel_res)
         if n_src <= p.gicp_min_num_points:
             return None                                              # "Low number of points in the cloud!" (odom.cc:764-767)
-        xyz = np.stack([records["x"], records["y"], records["z"]], 1)
-        ok = np.isfinite(xyz).all(1) & ~((np.abs(xyz) < p.crop_size).all(1))
-        self.computeSpaciousness(xyz[ok])
+        # original_scan = the cloud after removeNaN + CropBox (odom.cc:490-526); only its planar ranges are needed
+        x, y, z = (np.ascontiguousarray(records[f]) for f in ("x", "y", "z"))
+        c = np.float32(p.crop_size)
+        ok = np.isfinite(x + y + z) & ~((np.abs(x) < c) & (np.abs(y) < c) & (np.abs(z) < c))
+        self.computeSpaciousness(x[ok], y[ok])
         self.computeDensity()
         if p.adaptive:
             self.setAdaptiveParams()
@@ -344,13 +346,14 @@ OS1_RECORD = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), 
 
 def synthetic_sequence(scene, n_scans: int, seed: int = 0, step: float = 0.25, w: int = 1024, groups: int = 8, mulran: bool = False):
     """A seeded OS1-64 sequence at 10 Hz for BASELINE configs 4/5: yields (records, sensor poses at the `groups` column
-    blocks, column block of every column). The sensor moves DURING a scan: block g of columns is cast from the pose
-    interpolated at its time, so the deskew frames matter. mulran=True zeroes the time field (one deskew stamp,
+    blocks, column block of every column, column time stamps). The sensor moves DURING a scan: block g of columns is
+    cast from the pose interpolated at its time, so the deskew frames matter; it is at rest during scan 0, which the
+    reference does not deskew (odom.cc:656-664). mulran=True zeroes the time field (one deskew stamp,
     file_player_mulran/src/ROSThread.cpp:509-518)."""
     from . import synth
     rng = np.random.default_rng(seed)
     poses = synth.trajectory(scene, n_scans + 1, seed, step=step)
-    dirs = synth.ray_dirs(w).reshape(64, w, 3) if synth.ray_dirs(w).shape[0] == 64 * w else None
+    poses = [poses[0]] + poses                                          # scan 0: no motion
     col_t = (np.arange(w) * (100e6 / w)).astype(np.uint32)              # ns since the scan start (os_ros.cpp:135-151)
     block = np.minimum((np.arange(w) * groups) // w, groups - 1)
     for i in range(n_scans):
@@ -358,12 +361,10 @@ def synthetic_sequence(scene, n_scans: int, seed: int = 0, step: float = 0.25, w
         rel = np.linalg.inv(A) @ Bp
         rv = _rotvec(rel[:3, :3])
         Ts = [A @ synth.se3(rv * (g + 0.5) / groups, rel[:3, 3] * (g + 0.5) / groups) for g in range(groups)]
-        full = [synth.scan(scene, T, rng, w=w, keep_all=True).reshape(-1, w, 3) if dirs is None else None for T in Ts]
-        if dirs is not None:
-            full = [synth.scan(scene, T, rng, w=w, keep_all=True).reshape(64, w, 3) for T in Ts]
         pts = np.empty((64, w, 3), np.float32)
         for g in range(groups):
-            pts[:, block == g] = full[g][:, block == g]
+            full = synth.scan(scene, Ts[g], rng, w=w, keep_all=True).reshape(64, w, 3)
+            pts[:, block == g] = full[:, block == g]
         rec = np.zeros(64 * w, OS1_RECORD)
         flat = pts.reshape(-1, 3)
         rec["x"], rec["y"], rec["z"], rec["w"] = flat[:, 0], flat[:, 1], flat[:, 2], 1.0

@@ -139,4 +139,4 @@ def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params):
         assert np.abs(a.T[:3, :3] - b.T[:3, :3]).max() < 1e-5
     # and the loop tracks the truth: the drift of the prior is removed by the registration
     err = [np.abs(r.T[:3, 3] - s[1][groups // 2][:3, 3]).max() for r, s in zip(rg[1:], seq[1:])]
-    assert max(err) < 0.1    # the first keyframe is not deskewed (no motion assumed, odom.cc:656-664): a few cm of map bias
+    assert max(err) < 0.02
