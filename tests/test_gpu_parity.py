@@ -604,3 +604,68 @@ def test_deskewed_voxel_filtered_scan_registers_like_the_host_pipeline():
     Tg, To = g.align(), o.align()
     assert g.nr_iterations_ == o.nr_iterations_
     assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < POSE_T_TOL and rot_angle(Tg[:3, :3], To[:3, :3]) < POSE_R_TOL
+
+
+# ----------------------------------------------------------------------------------- k-NN table layouts, speculation
+@pytest.mark.parametrize("k,n", [(20, 4000), (16, 1001), (10, 1500), (32, 2000), (5, 777)])
+def test_covariances_other_k_and_ragged_sizes(k, n):
+    """k = 16 / 20 take the tiled k-NN table (partial last tile when n is not a multiple of 32), every other k the
+    row-major one (csrc/internal.h:nbr_tiled); the reference's default k is 20 (nano_gicp.cc:60)."""
+    a, _, _ = S.scan_pair(9, w=128)
+    a = a[np.sort(np.random.default_rng(k).choice(len(a), n, replace=False))]
+    g = S.configure(ngicp.NanoGICP(0), k=k)
+    o = S.configure(oracle.OracleGICP("port"), k=k)
+    g.setInputSource(a); o.setInputSource(a)
+    g.calculateSourceCovariances(); o.calculateSourceCovariances()
+    C, Co = g.getSourceCovariances(), o.getSourceCovariances()
+    idx, _ = oracle.KdTree(a, "port").knn(a, k)
+    ok = S.spectral_gap_ok(a, idx)
+    assert ok.sum() > n // 4 and np.abs(C - Co)[ok].max() < COV_RTOL
+    assert abs(g.source_density_ - o.source_density_) < 1e-4 * o.source_density_
+
+
+def _fresh_align(src, tgt, max_corr=0.5, guess=None, spec=None):
+    import os
+    old = os.environ.get("NGICP_K4_SPEC")
+    if spec is not None:
+        os.environ["NGICP_K4_SPEC"] = spec
+    try:
+        g = S.configure(ngicp.NanoGICP(0), max_corr=max_corr)
+    finally:
+        if spec is not None:
+            if old is None: os.environ.pop("NGICP_K4_SPEC")
+            else: os.environ["NGICP_K4_SPEC"] = old
+    g.setInputTarget(tgt); g.calculateTargetCovariances()
+    g.setInputSource(src); g.calculateSourceCovariances()
+    T = g.align(guess)
+    return T, g.nr_iterations_, g.getFinalError()
+
+
+def test_first_search_speculation_never_changes_the_result():
+    """calculateSourceCovariances starts the first correspondence search of the coming align at the identity pose on a
+    second stream. The result must be the one of a handle that never speculates, bit for bit, when it is used (identity
+    guess) and when it has to be thrown away: another guess, a target that changes in between (DLIO adopts a new submap
+    between setInputSource and align, reference src/dlio/src/dlio/odom.cc:989-1005), a new correspondence gate."""
+    a, b, _ = S.scan_pair(2, w=128)
+    c, _, _ = S.scan_pair(7, w=128)
+    guess = synth.se3((0.0, 0.01, -0.02), (0.05, -0.03, 0.01)).astype(np.float32)
+    for gs in (None, guess):
+        Ts, its, es = _fresh_align(b, a, guess=gs)
+        Tn, itn, en = _fresh_align(b, a, guess=gs, spec="0")
+        assert (Ts == Tn).all() and its == itn and es == en
+    # the target changes after the source covariances were computed
+    g = S.configure(ngicp.NanoGICP(0))
+    g.setInputTarget(c); g.calculateTargetCovariances()
+    g.setInputSource(b); g.calculateSourceCovariances()          # speculates against c
+    g.setInputTarget(a); g.calculateTargetCovariances()
+    T = g.align()
+    Tn, itn, en = _fresh_align(b, a, spec="0")
+    assert (T == Tn).all() and g.nr_iterations_ == itn and g.getFinalError() == en
+    # the gate changes after the source covariances were computed
+    g = S.configure(ngicp.NanoGICP(0), max_corr=1.0)
+    g.setInputTarget(a); g.calculateTargetCovariances()
+    g.setInputSource(b); g.calculateSourceCovariances()          # speculates with a 1.0 m gate
+    g.setMaxCorrespondenceDistance(0.25)
+    T = g.align()
+    Tn, itn, en = _fresh_align(b, a, max_corr=0.25, spec="0")
+    assert (T == Tn).all() and g.nr_iterations_ == itn and g.getFinalError() == en
