@@ -97,8 +97,10 @@ def test_rotation_only_keyframe_needs_no_neighbours():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("params", [odom.OdomParams(), odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5)], ids=["adaptive", "dense-keyframes"])
-def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params):
+@pytest.mark.parametrize("params,mulran", [(odom.OdomParams(), False), (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), False),
+                                           (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), True)],
+                         ids=["adaptive", "dense-keyframes", "mulran-shaped"])
+def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params, mulran):
     """BASELINE config 4 in miniature: the same seeded OS1-64 sequence (sensor moving during every scan, deskewed with
     per-stamp priors, voxel filtered, keyframes and submap rebuilt) through the loop over the CUDA path and through the
     loop over the CPU oracle: same keyframes, same submap sets, same iteration counts, poses within 1e-4 m / 1e-5 rad."""
@@ -106,8 +108,10 @@ def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params):
     import scenarios as S
     from odom_backends import OracleBackend
     scene = synth.Scene(3)
-    n, w, groups = 14, 256, 8
-    seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups))
+    # MulRan-shaped input (BASELINE config 5): every time stamp is zero, so a scan is one deskew group
+    # (file_player_mulran/src/ROSThread.cpp:509-518) and the sensor is taken to be at rest during a scan
+    n, w, groups = 14, 256, (1 if mulran else 8)
+    seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups, mulran=mulran))
     rng = np.random.default_rng(5)
     drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
 

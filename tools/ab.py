@@ -23,7 +23,7 @@ if sys.argv[1] == "k3":
     gg.setInputSource(a); o.setInputSource(a); gg.calculateSourceCovariances(); o.calculateSourceCovariances()
     idx, _ = oracle.KdTree(a, "port").knn(a, 16); ok = S.spectral_gap_ok(a, idx)
     err = np.abs(gg.getSourceCovariances() - o.getSourceCovariances())
-    print("K3", env, "cov_ms", round(out["covariance_ms"], 4), "frac", round(out["roofline_K3"]["frac"], 3),
+    print("K3", env, "index_ms", round(out["index_ms"], 3), "knn_ms", round(out["knn_ms"], 3), "cov_ms", round(out["covariance_ms"], 4), "frac", round(out["roofline_K3"]["frac"], 3),
           "err(gap-ok)", float(err[ok].max()), "err(all)", float(err.max()), "rows", int(ok.sum()), "/", len(ok))
 else:
     tgt, bounds, scans = bench.make_workload(0)
