@@ -148,15 +148,15 @@ int compute_covariances_impl(Handle* h, int which, float* density) {
     rc = knn_self(h, idx, k, d_nbr, d_dens);
   }
   if (!rc) {
-    StageTimer t(h, &h->t.covariance_ms);
-    rc = covariances_from_knn(h, idx, d_nbr, k, h->params.regularization, c.cov6);
-  }
-  if (!rc && density && idx->n_seg == 1) {
-    // density = sum / N (nano_gicp.cc:389): the kernel delivers the sum to host-mapped memory. Callers that do not
-    // need the value pass NULL and stay asynchronous.
+    // density = sum / N (nano_gicp.cc:389): K3 delivers the sum to host-mapped memory with the covariances. Callers that
+    // do not need the value pass NULL and stay asynchronous.
+    const bool want = density && idx->n_seg == 1;
     double sum = 0.0;
-    rc = reduce_sum(h, d_dens, (int)n, idx->seg_start, 1, &sum);
-    if (!rc) {
+    {
+      StageTimer t(h, &h->t.covariance_ms);
+      rc = covariances_from_knn(h, idx, d_nbr, k, h->params.regularization, c.cov6, want ? d_dens : nullptr, want ? &sum : nullptr);
+    }
+    if (!rc && want) {
       c.density = (float)(sum / (double)n);
       *density = c.density;
     }

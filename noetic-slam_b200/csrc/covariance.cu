@@ -11,6 +11,7 @@
 // All arithmetic is fp64 from fp32 inputs, as in the reference; output is 6 x fp32 per point.
 #include "internal.h"
 #include "eig3.cuh"
+#include "linearize.cuh"
 
 namespace ngicp {
 
@@ -157,10 +158,8 @@ __device__ __forceinline__ void covariance_from_ids(const float4* __restrict__ p
 
 // One thread per point. K = compile-time k (vector index loads, fully unrolled gathers) or 0 for a runtime k.
 template <int K, int REG>
-__global__ void __launch_bounds__(128) covariance_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
-                                                         float* __restrict__ cov6) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+__device__ __forceinline__ void covariance_point(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                 float* __restrict__ cov6, int j) {
   const float4 pj = __ldg(pts + j);
   if constexpr (K > 0) {
     // tiled k-NN table (internal.h:nbr_tiled): chunk c of the 32 points of a tile is contiguous, so a warp reads 512
@@ -190,6 +189,34 @@ __global__ void __launch_bounds__(128) covariance_kernel(const float4* __restric
     out[1] = make_float2((float)o.xz, (float)o.yy);
     out[2] = make_float2((float)o.yz, (float)o.zz);
   }
+}
+
+template <int K, int REG>
+__global__ void __launch_bounds__(128) covariance_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                         float* __restrict__ cov6) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) covariance_point<K, REG>(pts, nbr, n, k_rt, cov6, j);
+}
+
+// Single clouds: the density sum of nano_gicp.cc:389 (per-point terms from K2) rides on the same launch — block sums,
+// then the fixed-order fold and host-mapped result slot of K4b / K5 (linearize.cuh:block_publish) — instead of a reduction
+// kernel of its own behind K3.
+template <int K, int REG>
+__global__ void __launch_bounds__(kLinThreads) covariance_density_kernel(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k_rt,
+                                                                          float* __restrict__ cov6, const double* __restrict__ dens_term,
+                                                                          double* __restrict__ partials, unsigned int* __restrict__ counters,
+                                                                          ReduceSlot* __restrict__ slots, unsigned long long seq) {
+  __shared__ double wsum[kLinThreads / 32][1];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (j < n) {
+    v = __ldg(dens_term + j);
+    covariance_point<K, REG>(pts, nbr, n, k_rt, cov6, j);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][0] = v;
+  block_publish<1>(wsum, partials, counters, slots, seq);
 }
 
 // ---- layout conversions between the host's CovarianceList order and the device's sorted order ----
@@ -236,11 +263,19 @@ int cov6_from_host_order(Handle* h, const Index* idx, const float* d_in6, float*
   return NGICP_OK;
 }
 
-int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6) {
+int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6, const double* d_dens_term, double* density_sum) {
   const int n = idx->n;
   const int nb = (n + 127) / 128;
   cudaStream_t s = h->stream;
-#define LAUNCH_COV(K, REG) covariance_kernel<K, REG><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6)
+  // density fused into the launch when the block partials fit the handle's reduction buffers (single scans)
+  const bool fuse = d_dens_term && density_sum && idx->n_seg == 1 && nb <= kMaxLinBlocks;
+  const unsigned long long seq = fuse ? ++h->seq : 0ull;
+#define LAUNCH_COV(K, REG)                                                                                                              \
+  do {                                                                                                                                  \
+    if (fuse) covariance_density_kernel<K, REG><<<nb, kLinThreads, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6, d_dens_term, h->partials,     \
+                                                                           h->counter, h->slot_dev, seq);                              \
+    else covariance_kernel<K, REG><<<nb, 128, 0, s>>>(idx->pts, d_nbr, n, k, d_cov6);                                                   \
+  } while (0)
 #define LAUNCH_COV_K(REG)            \
   do {                               \
     if (k == 16) LAUNCH_COV(16, REG); \
@@ -259,6 +294,12 @@ int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, i
 #undef LAUNCH_COV
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
+  if (fuse) {
+    if (int rc = wait_slot(h, 1, seq)) return rc;
+    *density_sum = h->slot_host[0].v[0];
+  } else if (d_dens_term && density_sum && idx->n_seg == 1) {
+    if (int rc = reduce_sum(h, d_dens_term, n, idx->seg_start, 1, density_sum)) return rc;
+  }
   return NGICP_OK;
 }
 

@@ -135,7 +135,10 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
 // public k-NN: queries on device (float4), results in ORIGINAL indices, canonical order
 int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, int* d_out_idx, float* d_out_sqd);
 // K3. covariance + regularisation from the k-NN table
-int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6);
+// d_dens_term + density_sum (both optional, single-segment clouds): also delivers sum(d_dens_term) to the host (blocking)
+int covariances_from_knn(Handle* h, const Index* idx, const int* d_nbr, int k, int reg, float* d_cov6, const double* d_dens_term = nullptr,
+                         double* density_sum = nullptr);
+int wait_slot(Handle* h, int n_slots, unsigned long long seq);   // linearize.cu: spin on the host-mapped result slots
 // sum of n doubles -> *d_out (device), deterministic
 // deterministic per-segment sums of a device array, delivered to host memory (linearize.cu; blocks until they arrive)
 int reduce_sum(Handle* h, const double* d_in, int n, const int* seg_start_dev, int n_seg, double* host_out);

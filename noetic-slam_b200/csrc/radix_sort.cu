@@ -97,11 +97,19 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const unsign
     uint32_t row = 0;  // keys with this digit in earlier tiles
     if (rows_scanned) row = counts[threadIdx.x * nblocks + blockIdx.x];
     else {
+      // coalesced rows, sixteen loads in flight: the last tiles sum > 100 rows and this chain is the kernel's long pole
       int b = 0;
-      for (; b + 4 <= (int)blockIdx.x; b += 4)   // coalesced rows, four loads in flight
-        row += (counts[b * kSortRadix + threadIdx.x] + counts[(b + 1) * kSortRadix + threadIdx.x]) +
-               (counts[(b + 2) * kSortRadix + threadIdx.x] + counts[(b + 3) * kSortRadix + threadIdx.x]);
-      for (; b < (int)blockIdx.x; b++) row += counts[b * kSortRadix + threadIdx.x];
+      for (; b + 16 <= (int)blockIdx.x; b += 16) {
+        uint32_t v16[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) v16[u] = __ldg(counts + (b + u) * kSortRadix + threadIdx.x);
+#pragma unroll
+        for (int u = 0; u < 16; u++) row += v16[u];
+      }
+      for (; b + 4 <= (int)blockIdx.x; b += 4)
+        row += (__ldg(counts + b * kSortRadix + threadIdx.x) + __ldg(counts + (b + 1) * kSortRadix + threadIdx.x)) +
+               (__ldg(counts + (b + 2) * kSortRadix + threadIdx.x) + __ldg(counts + (b + 3) * kSortRadix + threadIdx.x));
+      for (; b < (int)blockIdx.x; b++) row += __ldg(counts + b * kSortRadix + threadIdx.x);
     }
     const uint32_t start = digit_base[threadIdx.x] - v;
     __syncthreads();
