@@ -344,32 +344,43 @@ OS1_RECORD = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), 
                        ("t", np.uint32), ("pad", np.uint32, 2)])      # 32 B, dlio::Point (include/dlio/dlio.h:85-108)
 
 
-def synthetic_sequence(scene, n_scans: int, seed: int = 0, step: float = 0.25, w: int = 1024, groups: int = 8, mulran: bool = False):
-    """A seeded OS1-64 sequence at 10 Hz for BASELINE configs 4/5: yields (records, sensor poses at the `groups` column
-    blocks, column block of every column, column time stamps). The sensor moves DURING a scan: block g of columns is
-    cast from the pose interpolated at its time, so the deskew frames matter; it is at rest during scan 0, which the
-    reference does not deskew (odom.cc:656-664). mulran=True zeroes the time field (one deskew stamp,
-    file_player_mulran/src/ROSThread.cpp:509-518)."""
+def synthetic_poses(scene, n_scans: int, seed: int = 0, step: float = 0.25):
+    """Sensor poses at the scan boundaries; the sensor is at rest during scan 0, which the reference does not deskew
+    (odom.cc:656-664)."""
     from . import synth
-    rng = np.random.default_rng(seed)
     poses = synth.trajectory(scene, n_scans + 1, seed, step=step)
-    poses = [poses[0]] + poses                                          # scan 0: no motion
+    return [poses[0]] + poses
+
+
+def synthetic_scan(scene, poses, i: int, seed: int = 0, w: int = 1024, groups: int = 8, mulran: bool = False):
+    """Scan i of a seeded OS1-64 sequence at 10 Hz (BASELINE configs 4/5): (records, sensor poses at the `groups` column
+    blocks, column block of every column, column time stamps). The sensor moves DURING the scan: block g of columns is
+    cast from the pose interpolated at its time, so the deskew frames matter. mulran=True zeroes the time field (one deskew
+    stamp, file_player_mulran/src/ROSThread.cpp:509-518). Every scan has its own seeded generator, so scans can be made in
+    any order (or in parallel)."""
+    from . import synth
+    rng = np.random.default_rng([seed, i])
     col_t = (np.arange(w) * (100e6 / w)).astype(np.uint32)              # ns since the scan start (os_ros.cpp:135-151)
     block = np.minimum((np.arange(w) * groups) // w, groups - 1)
+    A, Bp = poses[i], poses[i + 1]
+    rel = np.linalg.inv(A) @ Bp
+    rv = _rotvec(rel[:3, :3])
+    Ts = [A @ synth.se3(rv * (g + 0.5) / groups, rel[:3, 3] * (g + 0.5) / groups) for g in range(groups)]
+    pts = np.empty((64, w, 3), np.float32)
+    for g in range(groups):
+        full = synth.scan(scene, Ts[g], rng, w=w, keep_all=True).reshape(64, w, 3)
+        pts[:, block == g] = full[:, block == g]
+    rec = np.zeros(64 * w, OS1_RECORD)
+    flat = pts.reshape(-1, 3)
+    rec["x"], rec["y"], rec["z"], rec["w"] = flat[:, 0], flat[:, 1], flat[:, 2], 1.0
+    rec["t"] = 0 if mulran else np.broadcast_to(col_t[None], (64, w)).reshape(-1)
+    return rec, np.asarray(Ts, np.float64), block, col_t
+
+
+def synthetic_sequence(scene, n_scans: int, seed: int = 0, step: float = 0.25, w: int = 1024, groups: int = 8, mulran: bool = False):
+    poses = synthetic_poses(scene, n_scans, seed, step)
     for i in range(n_scans):
-        A, Bp = poses[i], poses[i + 1]
-        rel = np.linalg.inv(A) @ Bp
-        rv = _rotvec(rel[:3, :3])
-        Ts = [A @ synth.se3(rv * (g + 0.5) / groups, rel[:3, 3] * (g + 0.5) / groups) for g in range(groups)]
-        pts = np.empty((64, w, 3), np.float32)
-        for g in range(groups):
-            full = synth.scan(scene, Ts[g], rng, w=w, keep_all=True).reshape(64, w, 3)
-            pts[:, block == g] = full[:, block == g]
-        rec = np.zeros(64 * w, OS1_RECORD)
-        flat = pts.reshape(-1, 3)
-        rec["x"], rec["y"], rec["z"], rec["w"] = flat[:, 0], flat[:, 1], flat[:, 2], 1.0
-        rec["t"] = 0 if mulran else np.broadcast_to(col_t[None], (64, w)).reshape(-1)
-        yield rec, np.asarray(Ts, np.float64), block, col_t
+        yield synthetic_scan(scene, poses, i, seed, w, groups, mulran)
 
 
 def _rotvec(R) -> np.ndarray:

@@ -17,7 +17,16 @@ step = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
 groups = 2
 scene = synth.Scene(4)
 t0 = time.time()
-seq = list(odom.synthetic_sequence(scene, n, seed=4, step=step, w=1024, groups=groups))
+poses = odom.synthetic_poses(scene, n, 4, step)
+
+
+def make(i):
+    return odom.synthetic_scan(scene, poses, i, 4, 1024, groups)
+
+
+import multiprocessing as mp, os
+with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:      # before any CUDA context exists
+    seq = pool.map(make, range(n), chunksize=4)
 print(f"generated {n} scans in {time.time() - t0:.1f}s", flush=True)
 rng = np.random.default_rng(8)
 drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
@@ -41,6 +50,7 @@ def run(backend):
     return loop, res, ts
 
 
+import scipy.spatial  # noqa: F401  (the hull code imports it lazily; keep the one-off import out of the per-scan times)
 g = S.configure(ngicp.NanoGICP(0), max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)
 lg, rg, tg = run(odom.DeviceBackend(g))
 o = S.configure(oracle.OracleGICP("ref" if oracle.available("ref") else "port"), max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)
