@@ -101,3 +101,38 @@ def test_bulk_covariances_match_the_oracle(big):
         g1 = S.configure(ngicp.NanoGICP(0))
         g1.setInputSource(a); g1.calculateSourceCovariances()
         assert (g1.getSourceCovariances() == m4[off[i]:off[i + 1]]).all()
+
+
+def test_bulk_covariance_build_at_16m_points():
+    """BASELINE config 3 at its full size on one GPU: 256 keyframes x 65,536 points = 16,777,216 points in one batched
+    pass. Size-independent properties: PLANE spectrum {1, 1, 1e-3} on every row, keyframes never interact (a keyframe's rows
+    equal the rows it gets when it is the only cloud, bit for bit), per-keyframe densities equal the single-cloud ones."""
+    sc = synth.Scene(2)
+    rng = np.random.default_rng(21)
+    poses = synth.trajectory(sc, 8, 2, step=1.0)
+    base = [synth.transform_points(P, synth.scan(sc, P, rng, keep_all=True)) for P in poses]
+    clouds = []
+    for i in range(256):
+        T = synth.se3((0, 0, rng.uniform(-np.pi, np.pi)), rng.uniform(-5, 5, 3) * [1, 1, 0.05])
+        clouds.append(synth.transform_points(T, base[i % len(base)]))
+    pts = np.concatenate(clouds)
+    off = np.arange(257, dtype=np.int64) * 65536
+    assert len(pts) == 16_777_216
+    g = S.configure(ngicp.NanoGICP(0))
+    cov6, dens = g.batchCovariances(pts, off)
+    assert cov6.shape == (16_777_216, 6) and not np.isnan(cov6).any()
+    tr = cov6[:, 0] + cov6[:, 3] + cov6[:, 5]
+    assert np.abs(tr - 2.001).max() < 1e-5
+    sel = np.random.default_rng(0).choice(len(pts), 200_000, replace=False)
+    C = cov6[sel].astype(np.float64)
+    det = (C[:, 0] * (C[:, 3] * C[:, 5] - C[:, 4] ** 2) - C[:, 1] * (C[:, 1] * C[:, 5] - C[:, 4] * C[:, 2])
+           + C[:, 2] * (C[:, 1] * C[:, 4] - C[:, 3] * C[:, 2]))
+    assert np.abs(det - 1e-3).max() < 1e-6
+    for i in (0, 131, 255):
+        g1 = S.configure(ngicp.NanoGICP(0))
+        g1.setInputSource(clouds[i]); g1.calculateSourceCovariances()
+        C1 = g1.getSourceCovariances()
+        own = cov6[off[i]:off[i + 1]]
+        ref6 = np.stack([C1[:, 0, 0], C1[:, 0, 1], C1[:, 0, 2], C1[:, 1, 1], C1[:, 1, 2], C1[:, 2, 2]], 1).astype(np.float32)
+        assert (own == ref6).all()
+        assert abs(dens[i] - g1.source_density_) <= 1e-6 * abs(g1.source_density_)
