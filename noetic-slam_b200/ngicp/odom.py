@@ -263,8 +263,8 @@ class OdomLoop:
             return None                                              # "Low number of points in the cloud!" (odom.cc:764-767)
         # original_scan = the cloud after removeNaN + CropBox (odom.cc:490-526); only its planar ranges are needed
         x, y, z = (np.ascontiguousarray(records[f]) for f in ("x", "y", "z"))
-        c = np.float32(p.crop_size)
-        ok = np.isfinite(x + y + z) & ~((np.abs(x) < c) & (np.abs(y) < c) & (np.abs(z) < c))
+        m = np.maximum(np.maximum(np.abs(x), np.abs(y)), np.abs(z))       # NaN propagates and fails both comparisons
+        ok = (m >= np.float32(p.crop_size)) & (m < np.float32(np.inf))
         self.computeSpaciousness(x[ok], y[ok])
         self.computeDensity()
         if p.adaptive:
