@@ -90,6 +90,10 @@ __device__ __forceinline__ void write_tiled_row(const GridView& g, const TK& bes
   }
 }
 
+#ifdef NGICP_STATS
+__device__ unsigned long long g_k2_items[2 * 16384];   // development: start / end (globaltimer, ns) of every K2 work item
+#endif
+
 // Production K2: a warp owns 32/LPQ consecutive (Morton-sorted) points, LPQ lanes per point, shared staged
 // candidates (wknn.cuh).
 constexpr int kSelfWarps = 1;
@@ -104,7 +108,16 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
   if (active) { q = __ldg(g.pts + j); seg = find_segment(g.seg_start, g.n_seg, j); }
   TopK<K> best;
   uint32_t phase = wknn_init(scratch[threadIdx.x >> 5]);
+#ifdef NGICP_STATS
+  unsigned long long t_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
   warp_knn<LPQ>(g, active, q.x, q.y, q.z, seg, k, cmax, __int_as_float(0x7f800000), best, scratch[threadIdx.x >> 5], phase);
+#ifdef NGICP_STATS
+  if (threadIdx.x == 0 && blockIdx.x < 16384) {
+    unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    g_k2_items[2 * blockIdx.x] = t_start; g_k2_items[2 * blockIdx.x + 1] = t_end;
+  }
+#endif
   if (!active || (threadIdx.x & (LPQ - 1)) != 0) return;
   int* row = nbr + (size_t)j * k;
   if ((K == 16 || K == 20) && k == K && tiled) {
@@ -242,6 +255,11 @@ int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, i
 }  // namespace ngicp
 
 #ifdef NGICP_STATS
+extern "C" int ngicp_debug_items_knn(unsigned long long* out, int n_items) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_k2_items, sizeof(unsigned long long) * 2 * n_items);
+  return 0;
+}
 extern "C" int ngicp_debug_stats_knn(unsigned long long out[8], int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, ngicp::g_wknn_stats, sizeof(unsigned long long) * 8);

@@ -11,7 +11,7 @@ import subprocess
 from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parent.parent          # noetic-slam_b200/
-LIB_PATH = PKG_ROOT / "libngicp_b200.so"
+LIB_PATH = Path(os.environ["NGICP_LIB"]) if os.environ.get("NGICP_LIB") else PKG_ROOT / "libngicp_b200.so"   # NGICP_LIB: development builds (tools/)
 CSRC = PKG_ROOT / "csrc"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_LM_NOT_CONVERGED = range(6)
