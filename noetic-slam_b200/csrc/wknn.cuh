@@ -89,6 +89,9 @@ __device__ __forceinline__ void wknn_wait(WarpScratch& ws, int buf, uint32_t& ph
 // undefined, so persistent kernels that search many times keep one barrier and carry its phase parity along.)
 __device__ __forceinline__ uint32_t wknn_init(WarpScratch& ws) {
   if ((threadIdx.x & 31) == 0) { mbar_init(&ws.mbar[0], 1); mbar_init(&ws.mbar[1], 1); }
+#ifdef NGICP_STATS
+  if ((threadIdx.x & 31) == 0) { ws.pad[0] = 0; ws.pad[1] = 0; ws.pad[2] = 0; }
+#endif
   __syncwarp();
   return 0u;   // bit b = parity of the phase the next chunk staged into buffer b completes
 }
@@ -217,6 +220,9 @@ __device__ __forceinline__ void warp_knn(const GridView& g, bool active, float q
     __syncwarp();
     if (member) best.reset();
     WKNN_STAT(0, 1); WKNN_STAT(1, M); WKNN_STAT(2, __popc(__ballot_sync(FULL, member)));
+#ifdef NGICP_STATS
+    if (lane == 0) { ws.pad[0] += 1; ws.pad[1] += M; ws.pad[2] = max(ws.pad[2], M); }   // per work item: passes, staged candidates, largest pass
+#endif
 #ifdef NGICP_STATS
     if (lane == 0) { atomicMax(&g_wknn_stats[5], (unsigned long long)M); if (M > 2048) { atomicAdd(&g_wknn_stats[6], 1ull); atomicAdd(&g_wknn_stats[7], (unsigned long long)M); } }
 #endif

@@ -14,9 +14,10 @@ g = bench.configure(ngicp.NanoGICP(0))
 for rep in range(3):
     g.setInputSource(scans[rep]); g.calculateSourceCovariances()
 n_items = 8192
-buf = (ctypes.c_ulonglong * (2 * n_items))()
+buf = (ctypes.c_ulonglong * (4 * n_items))()
 L.ngicp_debug_items_knn(buf, n_items)
-a = np.array(buf[:], dtype=np.int64).reshape(n_items, 2)
+a = np.array(buf[:], dtype=np.int64).reshape(n_items, 4)
+passes, maxM, sumM = a[:, 2] >> 32, a[:, 2] & 0xffffffff, a[:, 3]
 t0 = a[:, 0].min()
 start, end = (a[:, 0] - t0) / 1e3, (a[:, 1] - t0) / 1e3     # us
 dur = end - start
@@ -25,7 +26,11 @@ print("sum of durations %.0f us -> %.1f us at 148*16 concurrent" % (dur.sum(), d
 order = np.argsort(-end)
 print("last items to finish: (index, start, duration)", [(int(i), round(float(start[i]), 1), round(float(dur[i]), 1)) for i in order[:10]])
 slow = np.argsort(-dur)[:20]
-print("slowest items: (index, start, duration)", [(int(i), round(float(start[i]), 1), round(float(dur[i]), 1)) for i in slow])
+print("slowest items: (index, start, duration, passes, sumM, maxM)", [(int(i), round(float(start[i]), 1), round(float(dur[i]), 1), int(passes[i]), int(sumM[i]), int(maxM[i])) for i in slow])
+print("all items: passes mean %.2f, sumM mean %.0f, maxM mean %.0f; corr(dur, sumM) %.3f corr(dur, passes) %.3f corr(dur, maxM) %.3f" % (passes.mean(), sumM.mean(), maxM.mean(), np.corrcoef(dur, sumM)[0, 1], np.corrcoef(dur, passes)[0, 1], np.corrcoef(dur, maxM)[0, 1]))
+for lo, hi in [(0, 15), (15, 25), (25, 40), (40, 60), (60, 200)]:
+    m = (dur >= lo) & (dur < hi)
+    if m.any(): print("  dur [%d,%d) us: %d items, passes %.1f, sumM %.0f, maxM %.0f" % (lo, hi, m.sum(), passes[m].mean(), sumM[m].mean(), maxM[m].mean()))
 # how many items are running over time
 ts = np.linspace(0, end.max(), 12)
 print("running items at t:", [(round(float(t), 0), int(((start <= t) & (end > t)).sum())) for t in ts])
