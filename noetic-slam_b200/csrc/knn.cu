@@ -94,43 +94,14 @@ __device__ __forceinline__ void write_tiled_row(const GridView& g, const TK& bes
 __device__ unsigned long long g_k2_items[4 * 16384];   // development: start / end (globaltimer, ns) of every K2 work item
 #endif
 
-// Launch order of the work items of a single scan. An item (one warp = 8 consecutive sorted points) takes 12-20 us where
-// the cloud is dense (one pass, ~200 staged candidates) and 60-100 us where a sparse group cell borders a dense one (several
-// passes, thousands of candidates); in index order the slow ones that start last leave the GPU a third empty for the last
-// 55 us of a 155 us kernel. The octree level of the smallest cell that holds the first and the last point of an item is a
-// free measure of sparsity (Morton keys are sorted): items are launched by descending level, so only dense, short items
-// are left for the end. One block: level histogram, prefix, scatter; the order inside a level is arbitrary and nothing
-// but the schedule depends on it.
-__global__ void __launch_bounds__(1024) k2_order_kernel(const unsigned long long* __restrict__ keys, int n, int per_item, int n_items,
-                                                        int* __restrict__ order) {
-  __shared__ int hist[32], cursor[32];
-  if (threadIdx.x < 32) hist[threadIdx.x] = 0;
-  __syncthreads();
-  auto level_of = [&](int it) {
-    const unsigned long long a = __ldg(keys + (size_t)it * per_item) >> 9, b = __ldg(keys + min(n - 1, it * per_item + per_item - 1)) >> 9;
-    const unsigned long long x = a ^ b;
-    return x ? min(31, (63 - __clzll((long long)x)) / 3 + 1) : 0;
-  };
-  for (int it = threadIdx.x; it < n_items; it += blockDim.x) atomicAdd(&hist[level_of(it)], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int l = 31; l >= 0; l--) { cursor[l] = run; run += hist[l]; }
-  }
-  __syncthreads();
-  for (int it = threadIdx.x; it < n_items; it += blockDim.x) order[atomicAdd(&cursor[level_of(it)], 1)] = it;
-}
-
 // Production K2: a warp owns 32/LPQ consecutive (Morton-sorted) points, LPQ lanes per point, shared staged
 // candidates (wknn.cuh).
 constexpr int kSelfWarps = 1;
 template <int K, int LPQ>
 __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView g, int k, int cmax, int normalization, bool tiled,
-                                                                        const int* __restrict__ item_order, int* __restrict__ nbr,
-                                                                        double* __restrict__ dens_term) {
+                                                                        int* __restrict__ nbr, double* __restrict__ dens_term) {
   __shared__ WarpScratch scratch[kSelfWarps];
-  const int item = item_order ? __ldg(item_order + blockIdx.x) : (int)blockIdx.x;   // sparse regions first (k2_order_kernel)
-  const int j = item * (blockDim.x / LPQ) + threadIdx.x / LPQ;
+  const int j = blockIdx.x * (blockDim.x / LPQ) + threadIdx.x / LPQ;
   const bool active = j < g.n;
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   int seg = 0;
@@ -245,19 +216,9 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   cudaStream_t s = h->stream;
   // lanes per query: small clouds need the extra warps, big ones prefer the sharing of one query per lane
   const int lpq = h->k2_lpq > 0 ? h->k2_lpq : (n < 1500000 ? 4 : 1);
-  // single scans: sparse items first (see k2_order_kernel); bulk builds run tens of waves and have no tail to speak of
-  static const int order_switch = getenv("NGICP_K2_ORDER") ? atoi(getenv("NGICP_K2_ORDER")) : 1;   // development switch
-  int* d_order = nullptr;
-  const int per_item = 32 * kSelfWarps / (lpq >= 4 ? 4 : 1);
-  const int n_items = (n + per_item - 1) / per_item;
-  if (order_switch && k <= 32 && idx->n_seg == 1 && n_items >= 148 * 16 && n_items <= (1 << 16)) {
-    NGICP_CUDA(h, dev_alloc(&d_order, (size_t)n_items, s));
-    k2_order_kernel<<<1, 1024, 0, s>>>(idx->keys, n, per_item, n_items, d_order);
-    count_launch(h);
-  }
 #define LAUNCH_SELF_L(K, LPQ)                                                                                             \
   knn_self_warp_kernel<K, LPQ><<<(n + (32 * kSelfWarps / LPQ) - 1) / (32 * kSelfWarps / LPQ), 32 * kSelfWarps, 0, s>>>( \
-      g, k, group_cap_for(k, h->k2_cmax_mult), normalization, nbr_tiled(k), d_order, d_nbr, d_dens_term)
+      g, k, group_cap_for(k, h->k2_cmax_mult), normalization, nbr_tiled(k), d_nbr, d_dens_term)
 #define LAUNCH_SELF(K) do { if (lpq >= 4) LAUNCH_SELF_L(K, 4); else LAUNCH_SELF_L(K, 1); } while (0)
   if (k == 1) LAUNCH_SELF(1);
   else if (k <= 8) LAUNCH_SELF(8);
@@ -267,7 +228,6 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   else knn_self_dyn_kernel<kMaxK><<<(n + 63) / 64, 64, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term);
 #undef LAUNCH_SELF
 #undef LAUNCH_SELF_L
-  dev_free(d_order, s);
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;
