@@ -30,31 +30,6 @@ __device__ __forceinline__ void self_query(const GridView& g, int j, int k, int 
   grid_knn(g, q.x, q.y, q.z, seg, k, start_count, __int_as_float(0x7f800000), best);
 }
 
-template <int K>
-__global__ void __launch_bounds__(128) knn_self_kernel(GridView g, int k, int start_count, int normalization, bool tiled,
-                                                       int* __restrict__ nbr, double* __restrict__ dens_term) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.n) return;
-  TopK<K> best;
-  self_query(g, j, k, start_count, normalization, nbr, dens_term, best);
-  int* row = nbr + (size_t)j * k;
-  if (k == K && (K % 4) == 0) {
-#pragma unroll
-    for (int i = 0; i < K; i += 4)
-      *nbr_chunk<K>(nbr, j, i / 4, tiled) = make_int4(topos(g, best.p[i]), topos(g, best.p[i + 1]), topos(g, best.p[i + 2]), topos(g, best.p[i + 3]));
-  } else {
-#pragma unroll
-    for (int i = 0; i < K; i++) if (i < k) row[i] = topos(g, best.p[i]);
-  }
-  if (dens_term) {
-    // nano_gicp.cc:345-346: accumulate(k_sq_distances.begin()+1, end, 0.0) / normalization
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 1; i < K; i++) if (i < k) acc += (double)best.d[i];
-    dens_term[j] = acc / (double)normalization;
-  }
-}
-
 // Rows of the tiled table keep neighbour 0 (the query itself) first and the other k-1 in ASCENDING SORTED POSITION, not
 // distance order: K3 sums over the set, and lane-adjacent (Morton-adjacent) queries then gather from nearby addresses with
 // the same instruction — 9.0 instead of 11.7 distinct 128-byte lines per warp gather on an OS1-64 scan, which is what
