@@ -158,9 +158,11 @@ class DeviceBackend:
         return self.gicp.ingestScan(records, time_field, crop=crop)
 
     def deskew_filter_set_source(self, frames, leaf):
-        cloud = self.gicp.deskewScan(frames, leaf=(leaf,) * 3 if leaf else None, set_source=True)
+        return len(self.gicp.deskewScan(frames, leaf=(leaf,) * 3 if leaf else None, set_source=True))
+
+    def calculate_source_covariances(self):
         self.gicp.calculateSourceCovariances()
-        return len(cloud), self.gicp.source_density_
+        return self.gicp.source_density_
 
     def align(self):
         T = self.gicp.align()
@@ -258,9 +260,11 @@ class OdomLoop:
         else:
             frames = np.asarray(prior_frames(stamps), np.float32)
             self.T_prior = frames[median].copy()
-        n_src, self.source_density_ = self.b.deskew_filter_set_source(frames, p.voxel_res)
+        n_src = self.b.deskew_filter_set_source(frames, p.voxel_res)
         if n_src <= p.gicp_min_num_points:
             return None                                              # "Low number of points in the cloud!" (odom.cc:764-767)
+        # the reference's order (odom.cc:769-779): metrics (the density is still the previous scan's), adaptive parameters,
+        # then the source covariances — which is also when the device path starts the first correspondence search
         # original_scan = the cloud after removeNaN + CropBox (odom.cc:490-526); only its planar ranges are needed
         x, y, z = (np.ascontiguousarray(records[f]) for f in ("x", "y", "z"))
         m = np.maximum(np.maximum(np.abs(x), np.abs(y)), np.abs(z))       # NaN propagates and fails both comparisons
@@ -269,6 +273,7 @@ class OdomLoop:
         self.computeDensity()
         if p.adaptive:
             self.setAdaptiveParams()
+        self.source_density_ = self.b.calculate_source_covariances()
         if first:
             self.initializeInputTarget()
             self.buildKeyframesAndSubmap(self.lidar_p)

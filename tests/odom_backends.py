@@ -25,8 +25,11 @@ class OracleBackend:
             cloud = v.filter()
         self._src = cloud
         self.gicp.setInputSource(cloud)
+        return len(cloud)
+
+    def calculate_source_covariances(self):
         self.gicp.calculateSourceCovariances()
-        return len(cloud), self.gicp.source_density_
+        return self.gicp.source_density_
 
     def align(self):
         T = self.gicp.align()
@@ -57,7 +60,8 @@ class FakeBackend:
 
     def set_max_correspondence_distance(self, d): self.max_corr.append(d)
     def ingest(self, records, time_field, crop): return np.arange(4, dtype=np.float64), len(records)
-    def deskew_filter_set_source(self, frames, leaf): return 1000, 0.1
+    def deskew_filter_set_source(self, frames, leaf): return 1000
+    def calculate_source_covariances(self): return 0.1
     def align(self): return self.corrections.pop(0), True, 3
     def capture_keyframe(self): self.captured += 1; return self.captured - 1
     def transform_keyframe(self, kf, T): self.transformed.append(kf)

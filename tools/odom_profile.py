@@ -22,7 +22,7 @@ drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
 acc = collections.defaultdict(float); cnt = collections.defaultdict(int); mx = collections.defaultdict(float)
 class Timed(odom.DeviceBackend):
     pass
-for name in ("set_max_correspondence_distance", "ingest", "deskew_filter_set_source", "align", "capture_keyframe", "transform_keyframe", "set_submap"):
+for name in ("set_max_correspondence_distance", "ingest", "deskew_filter_set_source", "calculate_source_covariances", "align", "capture_keyframe", "transform_keyframe", "set_submap"):
     def wrap(f, name=name):
         def w(self, *a, **k):
             t = time.perf_counter(); r = f(self, *a, **k); d = time.perf_counter() - t; acc[name] += d; cnt[name] += 1; mx[name] = max(mx[name], d); return r
