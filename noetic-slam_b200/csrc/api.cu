@@ -235,6 +235,19 @@ int ngicp_create(int device, ngicp_handle** out) {
   CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long keep = ~0ull;  // keep freed blocks cached: per-scan allocations become free-list hits
   CREATE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  {
+    // Reserve the workspace once per device and process: the first index of a large submap otherwise pays the growth of
+    // the pool (tens of ms measured in the odom loop) in the middle of a sequence. NGICP_POOL_RESERVE_MB overrides (0 = off).
+    static std::atomic<unsigned> reserved_mask{0};
+    const unsigned bit = 1u << (device & 31);
+    if (!(reserved_mask.fetch_or(bit) & bit)) {
+      size_t mb = 1024;
+      if (const char* e = std::getenv("NGICP_POOL_RESERVE_MB")) mb = (size_t)std::max(0, std::atoi(e));
+      void* blk = nullptr;
+      if (mb && cudaMallocAsync(&blk, mb << 20, h->stream) == cudaSuccess) cudaFreeAsync(blk, h->stream);
+      else cudaGetLastError();   // not fatal: the pool simply grows on demand
+    }
+  }
   CREATE_CUDA(cudaMalloc(&h->partials, sizeof(double) * 32 * kMaxLinBlocks));
   CREATE_CUDA(cudaMalloc(&h->counter, sizeof(unsigned int) * kMaxBatch));
   CREATE_CUDA(cudaMemset(h->counter, 0, sizeof(unsigned int) * kMaxBatch));
