@@ -82,17 +82,19 @@ def concave_hull_indices(P: np.ndarray, alpha: float) -> list[int]:
         tri = Delaunay(Q)
     except QhullError:
         return []
+    # circumradius of every simplex at once: 2 (V_i - V_0) . c = |V_i|^2 - |V_0|^2
+    S = tri.simplices
+    V = Q[S]                                                      # (m, d+1, d)
+    A = 2.0 * (V[:, 1:] - V[:, :1])
+    rhs = (V[:, 1:] ** 2).sum(2) - (V[:, :1] ** 2).sum(2)
+    det = np.linalg.det(A)
+    good = np.abs(det) > 1e-300
+    centre = np.zeros((len(S), Q.shape[1]))
+    if good.any():
+        centre[good] = np.linalg.solve(A[good], rhs[good][..., None])[..., 0]
+    keep = good & (np.linalg.norm(centre - V[:, 0], axis=1) <= alpha)
     faces: dict[tuple, int] = {}
-    for simplex in tri.simplices:
-        V = Q[simplex]
-        A = 2.0 * (V[1:] - V[0])
-        b = (V[1:] ** 2).sum(1) - (V[0] ** 2).sum()
-        try:
-            centre = np.linalg.solve(A, b)
-        except np.linalg.LinAlgError:
-            continue
-        if np.linalg.norm(centre - V[0]) > alpha:
-            continue
+    for simplex in S[keep]:
         for skip in range(len(simplex)):
             f = tuple(sorted(int(v) for i, v in enumerate(simplex) if i != skip))
             faces[f] = faces.get(f, 0) + 1
