@@ -225,7 +225,7 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    W, K = args.warmup, args.steps
+    W, K = max(3, args.warmup), args.steps     # never fewer than three warm-up steps (timing rules)
     # ---- value: device-resident input, CUDA events on the handle's stream
     sampler = ClockSampler(local_rank)
     iters = []
