@@ -1,11 +1,11 @@
-// Stable LSD radix sort, 8-bit digits, hand-written for sm_100a (no CUB/Thrust).
+// Stable LSD radix sort, 9-bit digits (radix_sort.cuh), hand-written for sm_100a (no CUB/Thrust).
 //
 // Per sort:   1 histogram kernel over all passes (digit totals do not depend on order)
 //             1 tiny scan kernel -> global start of every digit of every pass
 // Per pass:   count   : per-tile digit counts            counts[digit][tile]
 //             scanrow : exclusive scan of every digit row over tiles
 //             scatter : warp-synchronous stable ranking (match_any) + scatter
-// A tile is 256 threads x ITEMS keys (8, or 2 for small inputs); warp w of a tile owns the contiguous chunk of 32*ITEMS keys
+// A tile is 512 threads x ITEMS keys (4, or 1 for small inputs); warp w of a tile owns the contiguous chunk of 32*ITEMS keys
 // [w*32*ITEMS, (w+1)*32*ITEMS) so that (tile, warp, round, lane) order == input order, which makes the
 // scatter stable. All global reads are coalesced 256-byte warp rows.
 #include "radix_sort.cuh"
@@ -189,13 +189,14 @@ int radix_sort_pairs(unsigned long long* keys_a, uint32_t* vals_a, unsigned long
   unsigned long long* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; p++) {
     const int shift = low_bit + p * kSortRadixBits;
-    if (items == 2) {
-      sort_count_kernel<2><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
-      sort_scatter_kernel<2><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
-    } else {
-      sort_count_kernel<8><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
+    if (items == 1) {
+      sort_count_kernel<1><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
       if (scan_rows) sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
-      sort_scatter_kernel<8><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+      sort_scatter_kernel<1><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
+    } else {
+      sort_count_kernel<4><<<nblocks, kSortThreads, 0, stream>>>(kin, n, shift, counts, nblocks, scan_rows ? 1 : 0);
+      if (scan_rows) sort_scan_rows_kernel<<<kSortRadix, 256, 0, stream>>>(counts, nblocks);
+      sort_scatter_kernel<4><<<nblocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, counts, digit_hist + p * kSortRadix, n, shift, nblocks, scan_rows ? 1 : 0);
     }
     launches += scan_rows ? 3 : 2;
     unsigned long long* tk = kin; kin = kout; kout = tk;

@@ -7,14 +7,16 @@
 
 namespace ngicp {
 
-constexpr int kSortRadixBits = 8;
+// 9-bit digits: the 27 key bits of a single cloud's index (levels >= 3) sort in three passes instead of four. One thread
+// per digit in the count / scan steps, so a tile is 512 threads.
+constexpr int kSortRadixBits = 9;
 constexpr int kSortRadix = 1 << kSortRadixBits;
-constexpr int kSortThreads = 256;
-// keys per thread: 2 for small inputs (a 65,536-point scan becomes 128 tiles instead of 32 and reaches most SMs), 8 otherwise
-inline int sort_items_for(int n) { return n <= 131072 ? 2 : 8; }
+constexpr int kSortThreads = kSortRadix;
+// keys per thread: 1 for small inputs (a 65,536-point scan becomes 128 tiles instead of 32 and reaches most SMs), 4 otherwise
+inline int sort_items_for(int n) { return n <= 131072 ? 1 : 4; }
 inline int sort_num_blocks(int n) { const int tile = kSortThreads * sort_items_for(n); return (n + tile - 1) / tile; }
 inline int sort_num_passes(int nbits) { return (nbits + kSortRadixBits - 1) / kSortRadixBits; }
-// scratch (uint32 elements): per-pass digit totals [passes*256] + per-tile digit counts [256*tiles]
+// scratch (uint32 elements): per-pass digit totals [passes*radix] + per-tile digit counts [radix*tiles]
 inline size_t sort_scratch_elems(int n, int nbits) {
   return (size_t)sort_num_passes(nbits) * kSortRadix + (size_t)kSortRadix * sort_num_blocks(n) + 64;
 }
