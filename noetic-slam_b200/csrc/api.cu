@@ -131,6 +131,9 @@ int compute_covariances_impl(Handle* h, int which, float* density) {
   if (!idx) return fail(h, NGICP_ERR_INVALID, "calculate covariances: no cloud attached");
   const int k = h->params.k_correspondences;
   if (idx->n_seg == 1 && idx->n < k) return fail(h, NGICP_ERR_INVALID, "calculate covariances: fewer points than k_correspondences");
+  for (size_t sgm = 0; sgm + 1 < idx->seg_offsets_host.size(); sgm++)     // batched clouds: neighbours never cross a segment
+    if (idx->seg_offsets_host[sgm + 1] - idx->seg_offsets_host[sgm] < k)
+      return fail(h, NGICP_ERR_INVALID, "calculate covariances: a segment has fewer points than k_correspondences");
   cudaStream_t s = h->stream;
   const size_t n = idx->n;
   CovSet& c = h->covs[which];

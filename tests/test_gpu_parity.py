@@ -669,3 +669,14 @@ def test_first_search_speculation_never_changes_the_result():
     T = g.align()
     Tn, itn, en = _fresh_align(b, a, max_corr=0.25, spec="0")
     assert (T == Tn).all() and g.nr_iterations_ == itn and g.getFinalError() == en
+
+
+def test_batched_source_with_a_segment_smaller_than_k_is_an_error():
+    """Neighbours never cross a segment of a batched cloud, so a segment with fewer than k points cannot have k neighbours:
+    an error, like the single-cloud case (the reference leaves the tail of k_indices uninitialised, nanoflann_adaptor.h:145-146)."""
+    a, _, _ = S.scan_pair(4, w=64)
+    g = S.configure(ngicp.NanoGICP(0))
+    pts = np.concatenate([a[:2000], a[2000:2005], a[2005:4000]])
+    g.setInputSourceBatch(pts, np.array([0, 2000, 2005, len(pts)], np.int64))
+    with pytest.raises(RuntimeError):
+        g.calculateSourceCovariances()
