@@ -478,15 +478,6 @@ int swap_in_index(Handle* h, int which, Index* idx) {
   return NGICP_OK;
 }
 int select_device(Handle* h) { return use_device(h); }
-int stage_reserve(Handle* h, size_t bytes, void** host) {
-  if (int rc = ensure_stage(h, bytes)) return rc;
-  *host = h->stage_host;
-  return NGICP_OK;
-}
-int stage_sent(Handle* h) {
-  NGICP_CUDA(h, cudaEventRecord(h->stage_done, h->stream));
-  return NGICP_OK;
-}
 int upload_points(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats) {
   return upload_xyz(h, points, n, stride_bytes, d_xyz, stride_floats);
 }

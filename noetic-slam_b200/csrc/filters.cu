@@ -525,30 +525,6 @@ int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stri
   unsigned int* d_sums = nullptr;
   double* d_unique = nullptr;
   const int nb = ((int)n + kFiltThreads - 1) / kFiltThreads;
-  // Pageable records: x, y, z and the stamp are packed into the handle's page-locked staging buffer (16 or 24 bytes per
-  // point instead of the whole record) and copied from there; a pageable cudaMemcpyAsync of the 2 MB scan is a staged,
-  // synchronous copy that costs 0.25 ms. Page-locked records are copied as they are.
-  const void* src = points;
-  bool staged = false;
-  {
-    cudaPointerAttributes at;
-    const cudaError_t q = cudaPointerGetAttributes(&at, points);
-    if (q != cudaSuccess) cudaGetLastError();
-    const bool page_locked = q == cudaSuccess && at.type == cudaMemoryTypeHost;
-    if (!page_locked && stride_bytes > 12 + tsize) {
-      const size_t toff = tsize == 8 ? 16 : 12, pstride = toff + tsize;
-      void* st = nullptr;
-      if (int rc = stage_reserve(h, n * pstride, &st)) return rc;
-      const char* in = static_cast<const char*>(points);
-      char* out = static_cast<char*>(st);
-      for (size_t i = 0; i < n; i++) {
-        std::memcpy(out + i * pstride, in + i * stride_bytes, 12);
-        std::memcpy(out + i * pstride + toff, in + i * stride_bytes + time_offset_bytes, tsize);
-      }
-      src = st; staged = true;
-      stride_bytes = pstride; time_offset_bytes = toff;
-    }
-  }
   NGICP_CUDA(h, dev_alloc(&d_recs, n * stride_bytes, s));
   NGICP_CUDA(h, dev_alloc(&keys_a, n, s));
   NGICP_CUDA(h, dev_alloc(&keys_b, n, s));
@@ -558,8 +534,7 @@ int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stri
   NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 2, s));
   NGICP_CUDA(h, dev_alloc(&d_unique, n, s));
   NGICP_CUDA(h, dev_alloc(&h->scan_pts, n, s));
-  NGICP_CUDA(h, cudaMemcpyAsync(d_recs, src, n * stride_bytes, cudaMemcpyHostToDevice, s));
-  if (staged) { if (int rc = stage_sent(h)) return rc; }
+  NGICP_CUDA(h, cudaMemcpyAsync(d_recs, points, n * stride_bytes, cudaMemcpyHostToDevice, s));
   NGICP_CUDA(h, cudaMemsetAsync(sort_scratch, 0, sizeof(uint32_t) * passes * kSortRadix, s));
   ingest_keys_kernel<<<((int)n + 255) / 256, 256, 0, s>>>(d_recs, stride_bytes, time_offset_bytes, time_type, (int)n, box, crop_min ? 1 : 0, keys_a, vals_a,
                                                          sort_scratch, passes);

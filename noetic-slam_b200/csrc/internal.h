@@ -160,10 +160,6 @@ int transform_points_device(Handle* h, const float* d_xyz_in, int stride_floats,
 // bookkeeping shared with keyframe.cu
 int swap_in_index(Handle* h, int which, Index* idx);   // make idx the source/target cloud, drop that side's covariances
 int select_device(Handle* h);
-// page-locked staging buffer of the handle (api.cu): reserve >= bytes (waits for the previous copy out of it), then mark the
-// copy that was just enqueued from it
-int stage_reserve(Handle* h, size_t bytes, void** host);
-int stage_sent(Handle* h);
 
 // workspace helpers (stream-ordered pool)
 template <typename T>
