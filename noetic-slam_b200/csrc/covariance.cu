@@ -151,9 +151,9 @@ __device__ __forceinline__ void covariance_from_ids(const float4* __restrict__ p
   c.yy = (syy - sy * sy * ik) * ik; c.yz = (syz - sy * sz * ik) * ik; c.zz = (szz - sz * sz * ik) * ik;
   const Sym3 o = regularize<REG>(c);
   float2* out = reinterpret_cast<float2*>(cov6 + (size_t)j * 6);
-  out[0] = make_float2((float)o.xx, (float)o.xy);
-  out[1] = make_float2((float)o.xz, (float)o.yy);
-  out[2] = make_float2((float)o.yz, (float)o.zz);
+  __stcs(out, make_float2((float)o.xx, (float)o.xy));
+  __stcs(out + 1, make_float2((float)o.xz, (float)o.yy));
+  __stcs(out + 2, make_float2((float)o.yz, (float)o.zz));
 }
 
 // One thread per point. K = compile-time k (vector index loads, fully unrolled gathers) or 0 for a runtime k.
@@ -165,7 +165,8 @@ __device__ __forceinline__ void covariance_point(const float4* __restrict__ pts,
     // tiled k-NN table (internal.h:nbr_tiled): chunk c of the 32 points of a tile is contiguous, so a warp reads 512
     // contiguous bytes per load (4 L1 wavefronts instead of the 16 of a 64-byte-strided row read)
     const int4* tile = reinterpret_cast<const int4*>(nbr) + (size_t)(j >> 5) * (K / 4) * 32 + (j & 31);
-    covariance_from_ids<K, REG>(pts, pj, [&](int c) { return __ldg(tile + c * 32); }, cov6, j);
+    // the index rows are read once: streaming loads (evict-first) leave L1 / L2 to the gathered neighbour points
+    covariance_from_ids<K, REG>(pts, pj, [&](int c) { return __ldcs(tile + c * 32); }, cov6, j);
   } else {
     const int k = k_rt;
     // the table is tiled for the k that K2 writes tiled (internal.h:nbr_tiled), row-major otherwise
