@@ -144,3 +144,20 @@ def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params, mulran
     # and the loop tracks the truth: the drift of the prior is removed by the registration
     err = [np.abs(r.T[:3, 3] - s[1][groups // 2][:3, 3]).max() for r, s in zip(rg[1:], seq[1:])]
     assert max(err) < 0.02
+
+
+def test_synthetic_sequence_is_seeded_per_scan_and_shaped_like_the_reference_point():
+    """Records are the reference's 32-byte dlio::Point (include/dlio/dlio.h:85-108); every scan has its own seeded generator,
+    so scan i is the same whether it is made alone, in order, or in another process; MulRan-shaped scans carry zero stamps."""
+    assert odom.OS1_RECORD.itemsize == 32 and odom.OS1_RECORD.fields["t"][1] == 20
+    scene = synth.Scene(1)
+    poses = odom.synthetic_poses(scene, 4, seed=7, step=0.3)
+    assert np.array_equal(poses[0], poses[1])                                  # at rest during scan 0 (not deskewed, odom.cc:656-664)
+    seq = list(odom.synthetic_sequence(scene, 4, seed=7, step=0.3, w=64, groups=4))
+    rec2, Ts2, block, col_t = odom.synthetic_scan(scene, poses, 2, seed=7, w=64, groups=4)
+    assert rec2.tobytes() == seq[2][0].tobytes() and np.array_equal(Ts2, seq[2][1])
+    assert len(rec2) == 64 * 64 and (rec2["w"] == 1.0).all()
+    assert rec2["t"].max() == col_t.max() and len(np.unique(rec2["t"])) == 64   # one stamp per column (os_ros.cpp:135-151)
+    assert len(Ts2) == 4 and sorted(set(block.tolist())) == [0, 1, 2, 3]
+    mul, _, _, _ = odom.synthetic_scan(scene, poses, 2, seed=7, w=64, groups=1, mulran=True)
+    assert (mul["t"] == 0).all()                                               # file_player_mulran/src/ROSThread.cpp:509-518
