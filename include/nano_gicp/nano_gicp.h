@@ -68,7 +68,7 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     source_covs_.swap(target_covs_);
     check(ngicp_swap_source_and_target(h_));
     std::swap(attached_[0], attached_[1]);
-    std::swap(uploaded_covs_[0], uploaded_covs_[1]);
+    uploaded_covs_[0].swap(uploaded_covs_[1]);
     std::swap(device_covs_[0], device_covs_[1]);
   }
   virtual void clearSource() override { input_.reset(); source_covs_.reset(); device_covs_[0] = false; check(ngicp_clear(h_, NGICP_SOURCE)); attached_[0] = nullptr; }  // nano_gicp.cc:107-110
@@ -98,7 +98,7 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     size_t n_out = 0;
     check(ngicp_filter_scan(h_, raw->points.data(), raw->points.size(), sizeof(PointSource), crop_size > 0 ? mn : nullptr,
                             crop_size > 0 ? mx : nullptr, 1, leaf > 0 ? lf : nullptr, NGICP_SOURCE, xyz.data(), &n_out));
-    auto cloud = std::make_shared<pcl::PointCloud<PointSource>>();
+    PointCloudSourcePtr cloud(new PointCloudSource);   // PointCloud::Ptr is boost::shared_ptr up to PCL 1.10, std::shared_ptr from 1.11
     cloud->points.resize(n_out);
     for (size_t i = 0; i < n_out; i++) { cloud->points[i].x = xyz[3 * i]; cloud->points[i].y = xyz[3 * i + 1]; cloud->points[i].z = xyz[3 * i + 2]; }
     cloud->width = static_cast<std::uint32_t>(n_out); cloud->height = 1; cloud->is_dense = true;
@@ -106,13 +106,16 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     auto tree = std::make_shared<nanoflann::KdTreeFLANN<PointSource>>();
     tree->adopt(cloud, ngicp_get_index(h_, NGICP_SOURCE));
     attached_[NGICP_SOURCE] = tree->index();
-    uploaded_covs_[NGICP_SOURCE] = nullptr;
+    uploaded_covs_[NGICP_SOURCE].reset();
     source_kdtree_ = tree;
     source_covs_.reset();
     device_covs_[NGICP_SOURCE] = false;
     return cloud;
   }
   ngicp_handle* handle() const { return h_; }
+  // Additive: align(output) fills `output` with the transformed source as PCL does; a caller that never reads it
+  // (DLIO, odom.cc:1004-1005) can skip that host pass over the cloud.
+  void setComputeOutputCloud(bool on) { compute_output_ = on; }
   virtual void setSourceCovariances(const std::shared_ptr<const CovarianceList>& covs) { source_covs_ = covs; device_covs_[0] = false; }  // :164-166
   virtual void setTargetCovariances(const std::shared_ptr<const CovarianceList>& covs) { target_covs_ = covs; device_covs_[1] = false; }  // :169-171
   virtual void registerInputSource(const PointCloudSourceConstPtr& cloud) {   // nano_gicp.cc:119-124
@@ -150,9 +153,20 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
       const auto& covs = which == NGICP_SOURCE ? source_covs_ : target_covs_;
       if (!covs && !device_covs_[which]) device_covs_[which] = ngicp_has_covariances(h_, which, nullptr) != 0;
     }
-    // pcl::transformPointCloud(*input_, output, final_transformation_)  (lsq_registration.cc:133)
-    output = *input_;
-    check(ngicp_transform_source(h_, final_transformation_.data(), output.points.data(), output.points.size(), sizeof(PointSource)));
+    // pcl::transformPointCloud(*input_, output, final_transformation_)  (lsq_registration.cc:133). The cloud is the
+    // caller's host memory and every other field of a point is copied as it is, so this stays a host loop exactly like the
+    // reference's (fp32, ((m0 x + m1 y) + m2 z) + m3 per row); DLIO discards the result (odom.cc:1004-1005) and may switch
+    // it off with setComputeOutputCloud(false).
+    if (compute_output_) {
+      output = *input_;
+      const Matrix4& M = final_transformation_;
+      for (auto& pt : output.points) {
+        const float x = pt.x, y = pt.y, z = pt.z;
+        pt.x = ((M(0, 0) * x + M(0, 1) * y) + M(0, 2) * z) + M(0, 3);
+        pt.y = ((M(1, 0) * x + M(1, 1) * y) + M(1, 2) * z) + M(1, 3);
+        pt.z = ((M(2, 0) * x + M(2, 1) * y) + M(2, 2) * z) + M(2, 3);
+      }
+    }
   }
 
  public:
@@ -173,7 +187,7 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     auto tree = std::make_shared<nanoflann::KdTreeFLANN<PointSource>>();
     tree->adopt(cloud, ngicp_get_index(h_, which));
     attached_[which] = tree->index();
-    uploaded_covs_[which] = nullptr;
+    uploaded_covs_[which].reset();
     return tree;
   }
   bool calculate(int which) {
@@ -193,7 +207,7 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     auto covs = std::make_shared<CovarianceList>(n);
     check(ngicp_get_covariances(h_, which, (*covs)[0].data(), n));
     (which == NGICP_SOURCE ? source_covs_ : target_covs_) = covs;
-    uploaded_covs_[which] = covs.get();
+    uploaded_covs_[which] = covs;
     device_covs_[which] = false;
   }
   // DLIO assigns the public members directly (target_kdtree_ = submap_kdtree, odom.cc:995;
@@ -201,23 +215,26 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
   void sync_tree(int which) {
     const auto& tree = which == NGICP_SOURCE ? source_kdtree_ : target_kdtree_;
     ngicp_index* want = tree ? tree->index() : nullptr;
-    if (want != attached_[which]) { check(ngicp_attach_index(h_, which, want)); attached_[which] = want; uploaded_covs_[which] = nullptr; }
+    if (want != attached_[which]) { check(ngicp_attach_index(h_, which, want)); attached_[which] = want; uploaded_covs_[which].reset(); }
   }
   void sync() {
     check(ngicp_set_params(h_, &params_));
     for (int which = 0; which < 2; which++) {
       sync_tree(which);
       const auto& covs = which == NGICP_SOURCE ? source_covs_ : target_covs_;
-      if (covs && covs.get() != uploaded_covs_[which]) {
+      // uploaded_covs_ keeps the list it uploaded alive, so an address can never be reused by a different list (no ABA).
+      // The device stores covariances as 6 x fp32 (the reference keeps fp64 Matrix4d): user-supplied lists are rounded.
+      if (covs && covs != uploaded_covs_[which]) {
         check(ngicp_set_covariances(h_, which, (*covs)[0].data(), covs->size()));
-        uploaded_covs_[which] = covs.get();
+        uploaded_covs_[which] = covs;
       }
     }
   }
 
   ngicp_handle* h_ = nullptr;
   ngicp_index* attached_[2] = {nullptr, nullptr};
-  mutable const CovarianceList* uploaded_covs_[2] = {nullptr, nullptr};
+  mutable std::shared_ptr<const CovarianceList> uploaded_covs_[2];
+  bool compute_output_ = true;
   mutable bool device_covs_[2] = {false, false};   // covariances valid on the device, host list not materialised yet
 };
 

@@ -7,7 +7,11 @@
 #include <stdexcept>
 #include <vector>
 
+#include <pcl/pcl_config.h>
 #include <pcl/point_cloud.h>
+#if PCL_VERSION_COMPARE(<, 1, 11, 0)
+#include <boost/shared_ptr.hpp>   // PCL <= 1.10 (DLIO's Ubuntu 20.04 image) hands clouds and index lists around as boost::shared_ptr
+#endif
 
 #include "../ngicp_b200.h"
 
@@ -19,8 +23,18 @@ class KdTreeFLANN {
   typedef typename pcl::PointCloud<PointT> PointCloud;
   typedef typename pcl::PointCloud<PointT>::Ptr PointCloudPtr;
   typedef typename pcl::PointCloud<PointT>::ConstPtr PointCloudConstPtr;
+  // reference nanoflann_adaptor.h:66-69
+#if PCL_VERSION_COMPARE(<, 1, 11, 0)
+  typedef boost::shared_ptr<KdTreeFLANN<PointT>> Ptr;
+  typedef boost::shared_ptr<const KdTreeFLANN<PointT>> ConstPtr;
+  typedef boost::shared_ptr<std::vector<int>> IndicesPtr;
+  typedef boost::shared_ptr<const std::vector<int>> IndicesConstPtr;
+#else
+  typedef std::shared_ptr<KdTreeFLANN<PointT>> Ptr;
+  typedef std::shared_ptr<const KdTreeFLANN<PointT>> ConstPtr;
   typedef std::shared_ptr<std::vector<int>> IndicesPtr;
   typedef std::shared_ptr<const std::vector<int>> IndicesConstPtr;
+#endif
 
   explicit KdTreeFLANN(bool /*sorted*/ = false, int device = 0) : device_(device) {}
   ~KdTreeFLANN() {
@@ -64,6 +78,32 @@ class KdTreeFLANN {
     int found = 0;
     while (found < k && k_indices[found] >= 0) found++;
     return found;
+  }
+  // nanoflann_adaptor.h:155-174 (unused by GICP). As in the reference, `radius` bounds the SQUARED distance (it is handed to
+  // nanoflann's RadiusResultSet as is) and the test is strict; results come back sorted by (distance, index).
+  int radiusSearch(const PointT& point, double radius, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const {
+    k_indices.clear();
+    k_sqr_distances.clear();
+    if (!cloud_ || cloud_->points.empty()) return 0;
+    if (!index_) throw std::runtime_error("[nanoflann] findNeighbors() called before building the index.");
+    const_cast<KdTreeFLANN*>(this)->ensure_handle();
+    const size_t n = ngicp_index_size(index_);
+    for (size_t k = 32;; k *= 4) {      // exact k-NN with a growing k until the k-th neighbour falls outside the radius
+      if (k > n) k = n;
+      if (k > 128) k = 128;             // ngicp_knn serves k <= 128
+      std::vector<int> idx(k);
+      std::vector<float> sqd(k);
+      if (ngicp_knn(handle_, index_, &point, 1, sizeof(PointT), (int)k, idx.data(), sqd.data()) != NGICP_OK)
+        throw std::runtime_error(ngicp_last_error(handle_));
+      size_t found = 0;
+      while (found < k && idx[found] >= 0 && (double)sqd[found] < radius) found++;
+      if (found < k || k == n || k == 128) {
+        if (found == k && k == 128 && n > 128) throw std::runtime_error("KdTreeFLANN(b200)::radiusSearch: more than 128 points inside the radius");
+        k_indices.assign(idx.begin(), idx.begin() + found);
+        k_sqr_distances.assign(sqd.begin(), sqd.begin() + found);
+        return (int)found;
+      }
+    }
   }
   ngicp_index* index() const { return index_; }
 

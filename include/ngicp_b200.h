@@ -74,6 +74,15 @@ int ngicp_create(int device, ngicp_handle** out);
 int ngicp_destroy(ngicp_handle* h);
 int ngicp_set_params(ngicp_handle* h, const ngicp_params* p);
 int ngicp_get_params(const ngicp_handle* h, ngicp_params* p);
+/* Host clouds and their lifetime. Every entry point that takes a host cloud (ngicp_set_input, ngicp_set_input_batch,
+ * ngicp_index_build, ngicp_knn, ngicp_batch_covariances, ngicp_filter_scan, ngicp_scan_ingest) is done with the caller's
+ * buffer when it returns: pageable memory is packed into the handle's own staging buffer, page-locked memory
+ * (cudaHostAlloc / cudaHostRegister; stride <= 32 bytes) is copied straight out of the caller's buffer and the call
+ * waits for that copy (not for the kernels behind it). ngicp_set_async_input(h, 1) drops that wait for page-locked clouds:
+ * ngicp_set_input / ngicp_filter_scan then return with the copy in flight and the buffer must stay unchanged until the
+ * next call on this handle that synchronises (ngicp_compute_covariances with a density pointer, ngicp_align,
+ * ngicp_synchronize) — the reference keeps a pointer to the caller's cloud for just as long (nano_gicp.cc:141). */
+int ngicp_set_async_input(ngicp_handle* h, int on);
 /* the handle's cudaStream_t (as void*), for callers that want to order their own work after it */
 void* ngicp_stream(ngicp_handle* h);
 int ngicp_synchronize(ngicp_handle* h);
@@ -95,6 +104,12 @@ size_t ngicp_index_size(const ngicp_index* idx);
  * out_idx / out_sqd: nq x k, original point indices; rows with fewer than k hits padded with -1 / +inf. */
 int ngicp_knn(ngicp_handle* h, const ngicp_index* idx, const void* queries, size_t nq, size_t stride_bytes,
               int k, int32_t* out_idx, float* out_sqd);
+/* Inspection: the neighbour sets the covariance stage works on — the k_indices of nearestKSearch(cloud[i], k) inside
+ * calculate_covariances (nano_gicp.cc:343) — produced by the production search (K2, leaf-scheduled). out_idx: n x k
+ * original indices, row i = point i: the point itself first, then its other k-1 nearest neighbours in unspecified
+ * order (the SET is exact under the (distance, index) tie-break). out_density_terms (optional, n doubles):
+ * sum_{j>=1} d2_j / ((k-1)(k+2)/2) per point, the summand of nano_gicp.cc:345-347,389. */
+int ngicp_self_neighbours(ngicp_handle* h, int which, int k, int32_t* out_idx, double* out_density_terms);
 /* the 64-bit voxel key of every point in ORIGINAL order (spec in DESIGN.md §keys; bit-exact vs oracle) */
 int ngicp_index_keys(ngicp_handle* h, const ngicp_index* idx, uint64_t* out_keys, float origin_h0[4]);
 

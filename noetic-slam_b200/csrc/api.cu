@@ -12,8 +12,15 @@
 #include "internal.h"
 #include "linearize.cuh"
 #include "lm_host.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace ngicp {
+
+// Targets up to this size get the fine index levels too (scan-to-scan targets have their covariances computed by K2); a
+// submap's covariances come from its keyframes (odom.cc:1719-1729), so its table stays small for the correspondence search.
+constexpr size_t kFineTargetMax = 262144;
 
 static thread_local std::string g_thread_err;
 void set_thread_error(const std::string& s) { g_thread_err = s; }
@@ -59,11 +66,31 @@ int ensure_stage(Handle* h, size_t bytes) {
   return NGICP_OK;
 }
 
-// host AoS (xyz at floats 0..2 of every `stride_bytes` record) -> device. Pageable memory is packed into the pinned
-// staging buffer first (3 floats per point on the device). Page-locked memory (cudaHostAlloc / cudaHostRegister) with
-// a stride of at most 32 bytes is copied as it is, asynchronously and without touching it on the CPU; the kernels
-// read it with its stride (*stride_floats). Such a buffer must stay unchanged until the next call that synchronises
-// (covariances with a density, align) — the reference keeps a pointer to the caller's cloud for just as long.
+// host AoS (xyz at floats 0..2 of every `stride_bytes` record) -> device.
+//  * Page-locked memory (cudaHostAlloc / cudaHostRegister) with a stride of at most 32 bytes is copied as it is,
+//    asynchronously and without touching it on the CPU; the kernels read it with its stride (*stride_floats). The copy
+//    is still in flight when this function returns: the public entry points call finish_input() before THEY return
+//    (unless the caller opted into ngicp_set_async_input, include/ngicp_b200.h).
+//  * Pageable memory (what PCL clouds are) is packed to 12 bytes per point into the handle's pinned staging buffer in
+//    four slices, each slice's H2D copy leaving while the next one is packed; the caller's buffer is not referenced
+//    after return.
+void pack_xyz(float* __restrict__ st, const char* __restrict__ src, size_t n, size_t stride_bytes) {
+#if defined(__SSE2__)
+  // one unaligned 16-byte load and store per point (the 4th lane is overwritten by the next point's x)
+  if (stride_bytes >= 16 && n > 1) {
+    size_t i = 0;
+    for (; i + 1 < n; i++) _mm_storeu_ps(st + 3 * i, _mm_loadu_ps(reinterpret_cast<const float*>(src + i * stride_bytes)));
+    const float* p = reinterpret_cast<const float*>(src + i * stride_bytes);
+    st[3 * i] = p[0]; st[3 * i + 1] = p[1]; st[3 * i + 2] = p[2];
+    return;
+  }
+#endif
+  for (size_t i = 0; i < n; i++) {
+    const float* p = reinterpret_cast<const float*>(src + i * stride_bytes);
+    st[3 * i] = p[0]; st[3 * i + 1] = p[1]; st[3 * i + 2] = p[2];
+  }
+}
+
 int upload_xyz(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats = nullptr) {
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(h, NGICP_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
   if (stride_floats) {
@@ -74,6 +101,8 @@ int upload_xyz(Handle* h, const void* points, size_t n, size_t stride_bytes, flo
     if (q == cudaSuccess && at.type == cudaMemoryTypeHost && stride_bytes <= 32) {
       NGICP_CUDA(h, dev_alloc(d_xyz, n * (stride_bytes / 4), h->stream));
       NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz, points, n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+      NGICP_CUDA(h, cudaEventRecord(h->input_copied, h->stream));
+      h->input_pending = true;
       *stride_floats = (int)(stride_bytes / 4);
       return NGICP_OK;
     }
@@ -81,17 +110,26 @@ int upload_xyz(Handle* h, const void* points, size_t n, size_t stride_bytes, flo
   if (int rc = ensure_stage(h, n * 12)) return rc;
   float* st = static_cast<float*>(h->stage_host);
   const char* src = static_cast<const char*>(points);
+  NGICP_CUDA(h, dev_alloc(d_xyz, n * 3, h->stream));
   if (stride_bytes == 12) {
     std::memcpy(st, src, n * 12);
+    NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz, st, n * 12, cudaMemcpyHostToDevice, h->stream));
   } else {
-    for (size_t i = 0; i < n; i++) {
-      const float* p = reinterpret_cast<const float*>(src + i * stride_bytes);
-      st[3 * i] = p[0]; st[3 * i + 1] = p[1]; st[3 * i + 2] = p[2];
+    const size_t slices = n >= 16384 ? 4 : 1, per = (n + slices - 1) / slices;
+    for (size_t a = 0; a < n; a += per) {
+      const size_t m = std::min(per, n - a);
+      pack_xyz(st + 3 * a, src + a * stride_bytes, m, stride_bytes);
+      NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz + 3 * a, st + 3 * a, m * 12, cudaMemcpyHostToDevice, h->stream));
     }
   }
-  NGICP_CUDA(h, dev_alloc(d_xyz, n * 3, h->stream));
-  NGICP_CUDA(h, cudaMemcpyAsync(*d_xyz, st, n * 12, cudaMemcpyHostToDevice, h->stream));
   NGICP_CUDA(h, cudaEventRecord(h->stage_done, h->stream));
+  return NGICP_OK;
+}
+
+// called by the public entry points that took a host cloud, right before they return
+int finish_input(Handle* h) {
+  if (h->input_pending && !h->async_input) NGICP_CUDA(h, cudaEventSynchronize(h->input_copied));
+  h->input_pending = false;
   return NGICP_OK;
 }
 
@@ -220,6 +258,8 @@ int ngicp_create(int device, ngicp_handle** out) {
   if (const char* e = std::getenv("NGICP_K2_CMAX_MULT")) h->k2_cmax_mult = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("NGICP_K2_LPQ")) h->k2_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_LPQ")) h->k4_lpq = std::atoi(e);
+  if (const char* e = std::getenv("NGICP_K2_LEAF")) h->k2_leaf = std::atoi(e);
+  if (const char* e = std::getenv("NGICP_K2_CHUNK")) h->k2_chunk = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_BALL")) h->k4_ball = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_SPEC")) h->k4_spec = std::atoi(e);
   for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // setIdentity, lsq_registration.cc:65
@@ -261,6 +301,8 @@ int ngicp_create(int device, ngicp_handle** out) {
   CREATE_CUDA(cudaEventCreate(&h->ev[1]));
   CREATE_CUDA(cudaEventCreate(&h->ev[2]));
   CREATE_CUDA(cudaEventCreateWithFlags(&h->stage_done, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&h->input_copied, cudaEventDisableTiming));
+  if (const char* e = std::getenv("NGICP_ASYNC_INPUT")) h->async_input = std::atoi(e) != 0;
 #undef CREATE_CUDA
   *out = p;
   return NGICP_OK;
@@ -287,6 +329,7 @@ int ngicp_destroy(ngicp_handle* p) {
   if (h->scan_keys) cudaFree(h->scan_keys);
   if (h->heavy) cudaFree(h->heavy);
   if (h->heavy_count) cudaFree(h->heavy_count);
+  if (h->k2_ctr) cudaFree(h->k2_ctr);
   if (h->partials) cudaFree(h->partials);
   if (h->batch_partials) cudaFree(h->batch_partials);
   if (h->counter) cudaFree(h->counter);
@@ -296,6 +339,7 @@ int ngicp_destroy(ngicp_handle* p) {
   if (h->ev[1]) cudaEventDestroy(h->ev[1]);
   if (h->ev[2]) cudaEventDestroy(h->ev[2]);
   if (h->stage_done) cudaEventDestroy(h->stage_done);
+  if (h->input_copied) cudaEventDestroy(h->input_copied);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete p;
   return NGICP_OK;
@@ -305,13 +349,23 @@ int ngicp_set_params(ngicp_handle* p, const ngicp_params* prm) {
   if (!p || !prm) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_set_params: NULL argument");
   if (prm->k_correspondences < 1) return fail(H(p), NGICP_ERR_INVALID, "k_correspondences must be >= 1");
   if (prm->regularization < 0 || prm->regularization > NGICP_REG_FROBENIUS) return fail(H(p), NGICP_ERR_INVALID, "unknown regularization method");
-  drop_speculation(H(p));   // a search in flight used the old gate
+  // a speculative search in flight (api.cu:compute_covariances_impl, ngicp_align) used the old gate: only a change of
+  // the parameters the search depends on invalidates it — the drop-in header pushes the whole set before every align
+  if (prm->max_corr_dist != H(p)->params.max_corr_dist || prm->k_correspondences != H(p)->params.k_correspondences) {
+    if (int rc = use_device(H(p))) return rc;
+    drop_speculation(H(p));
+  }
   H(p)->params = *prm;
   return NGICP_OK;
 }
 int ngicp_get_params(const ngicp_handle* p, ngicp_params* prm) {
   if (!p || !prm) return NGICP_ERR_INVALID;
   *prm = p->params;
+  return NGICP_OK;
+}
+int ngicp_set_async_input(ngicp_handle* p, int on) {
+  if (!p) return NGICP_ERR_INVALID;
+  H(p)->async_input = on != 0;
   return NGICP_OK;
 }
 void* ngicp_stream(ngicp_handle* p) { return p ? (void*)H(p)->stream : nullptr; }
@@ -374,6 +428,7 @@ int ngicp_knn(ngicp_handle* p, const ngicp_index* idx, const void* queries, size
   if (!queries) return fail(h, NGICP_ERR_INVALID, "ngicp_knn: NULL queries");
   if (int rc = use_device(h)) return rc;
   cudaStream_t s = h->stream;
+  NGICP_CUDA(h, order_after_build(idx, s));
   float* d_xyz = nullptr;
   if (int rc = upload_xyz(h, queries, nq, stride_bytes, &d_xyz)) return rc;
   float4* d_q = nullptr; int* d_i = nullptr; float* d_d = nullptr;
@@ -396,12 +451,47 @@ int ngicp_knn(ngicp_handle* p, const ngicp_index* idx, const void* queries, size
   return rc;
 }
 
+int ngicp_self_neighbours(ngicp_handle* p, int which, int k, int32_t* out_idx, double* out_density_terms) {
+  if (!p || (which != 0 && which != 1) || !out_idx) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_self_neighbours: bad argument");
+  Handle* h = H(p);
+  if (int rc = use_device(h)) return rc;
+  const Index* idx = h->index[which];
+  if (!idx) return fail(h, NGICP_ERR_INVALID, "ngicp_self_neighbours: no cloud attached");
+  if (idx->n_seg == 1 && idx->n < k) return fail(h, NGICP_ERR_INVALID, "ngicp_self_neighbours: fewer points than k");
+  cudaStream_t s = h->stream;
+  const size_t n = (size_t)idx->n;
+  int *d_nbr = nullptr, *d_out = nullptr;
+  double* d_dens = nullptr;
+  NGICP_CUDA(h, dev_alloc(&d_nbr, nbr_elems(n, k), s));
+  NGICP_CUDA(h, dev_alloc(&d_out, n * (size_t)k, s));
+  NGICP_CUDA(h, dev_alloc(&d_dens, n, s));
+  int rc = knn_self(h, idx, k, d_nbr, d_dens);
+  if (!rc) rc = export_self_rows(h, idx, d_nbr, k, d_out);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out_idx, d_out, sizeof(int) * n * k, cudaMemcpyDeviceToHost, s);
+    // density terms are in sorted order on the device; hand them back per ORIGINAL point through the inverse permutation on the host
+    std::vector<double> dens;
+    std::vector<int> inv;
+    if (e == cudaSuccess && out_density_terms) {
+      dens.resize(n); inv.resize(n);
+      e = cudaMemcpyAsync(dens.data(), d_dens, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(inv.data(), idx->inv, sizeof(int) * n, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(h, NGICP_ERR_CUDA, std::string("ngicp_self_neighbours: ") + cudaGetErrorString(e));
+    else if (out_density_terms) for (size_t i = 0; i < n; i++) out_density_terms[i] = dens[inv[i]];
+  }
+  dev_free(d_nbr, s); dev_free(d_out, s); dev_free(d_dens, s);
+  return rc;
+}
+
 int ngicp_index_keys(ngicp_handle* p, const ngicp_index* idx, uint64_t* out_keys, float origin_h0[4]) {
   if (!p || !idx) return fail(p ? H(p) : nullptr, NGICP_ERR_INVALID, "ngicp_index_keys: NULL argument");
   Handle* h = H(p);
   if (int rc = use_device(h)) return rc;
   cudaStream_t s = h->stream;
   const Index& ix = *idx;
+  NGICP_CUDA(h, order_after_build(idx, s));
   if (out_keys) {
     unsigned long long* d_out = nullptr;
     NGICP_CUDA(h, dev_alloc(&d_out, (size_t)ix.n, s));
@@ -431,6 +521,7 @@ int ngicp_attach_index(ngicp_handle* p, int which, ngicp_index* idx) {
   if (old == idx) return NGICP_OK;
   drop_speculation(h);
   NGICP_CUDA(h, cudaStreamSynchronize(h->stream));  // our pending work may still read the old index
+  NGICP_CUDA(h, order_after_build(idx, h->stream)); // the index may still be under construction on its builder's stream
   CovSet& c = h->covs[which];
   if (c.valid) {
     // The reference keeps covariances across registerInput* / tree hand-over (nano_gicp.cc:119-132),
@@ -481,6 +572,7 @@ int select_device(Handle* h) { return use_device(h); }
 int upload_points(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats) {
   return upload_xyz(h, points, n, stride_bytes, d_xyz, stride_floats);
 }
+int finish_input_copy(Handle* h) { return finish_input(h); }
 }  // namespace ngicp
 }  // extern "C++"
 
@@ -493,10 +585,11 @@ int ngicp_set_input(ngicp_handle* p, int which, const void* points, size_t n, si
   int stride = 3;
   if (int rc = upload_xyz(h, points, n, stride_bytes, &d_xyz, &stride)) return rc;
   Index* idx = nullptr;
-  const int rc = build_index(h, d_xyz, stride, (int)n, nullptr, 1, &idx);
+  int rc = build_index(h, d_xyz, stride, (int)n, nullptr, 1, &idx, which == NGICP_SOURCE || n <= kFineTargetMax);
   dev_free(d_xyz, h->stream);
-  if (rc) return rc;
-  return swap_in_index(h, which, idx);
+  if (!rc) rc = swap_in_index(h, which, idx);
+  const int rc2 = finish_input(h);     // the caller's page-locked buffer is free again when this returns (see ngicp_set_async_input)
+  return rc ? rc : rc2;
 }
 
 int ngicp_set_input_device(ngicp_handle* p, int which, const void* d_points_f4, size_t n) {
@@ -505,13 +598,14 @@ int ngicp_set_input_device(ngicp_handle* p, int which, const void* d_points_f4, 
   if (!d_points_f4 || n == 0) return fail(h, NGICP_ERR_INVALID, "ngicp_set_input_device: empty cloud");
   if (int rc = use_device(h)) return rc;
   Index* idx = nullptr;
-  if (int rc = build_index(h, static_cast<const float*>(d_points_f4), 4, (int)n, nullptr, 1, &idx)) return rc;
+  if (int rc = build_index(h, static_cast<const float*>(d_points_f4), 4, (int)n, nullptr, 1, &idx, which == NGICP_SOURCE || n <= kFineTargetMax)) return rc;
   return swap_in_index(h, which, idx);
 }
 
 int ngicp_swap_source_and_target(ngicp_handle* p) {
   if (!p) return NGICP_ERR_INVALID;
   Handle* h = H(p);
+  if (int rc = use_device(h)) return rc;
   drop_speculation(h);
   std::swap(h->index[0], h->index[1]);
   std::swap(h->covs[0], h->covs[1]);

@@ -19,8 +19,8 @@ constexpr int kMortonBits = 3 * kBitsPerAxis;     // 36
 constexpr int kTopLevel = kBitsPerAxis;           // one cell spans the whole grid at this level
 constexpr int kNumLevels = kTopLevel + 1;         // levels 0..12
 constexpr int kMaxSegBits = 20;                   // keyframes per batched index
-constexpr int kSortLevel = 3;                     // keys are sorted on the bits of levels >= 3 only (27 of 36 bits):
-                                                  // one radix pass less; cells finer than that are never needed
+constexpr int kSortLevel = 0;                     // keys are sorted on all 36 bits (four 9-bit passes): where a scan is dense (the
+                                                  // returns next to the sensor) the self k-NN needs cells finer than the base level
 constexpr int kMaxCoord = (1 << kBitsPerAxis) - 1;
 constexpr unsigned long long kEmptyKey = ~0ull;
 
@@ -35,11 +35,13 @@ struct GridMeta {
   float h0;          // level-0 cell side, a power of two
   float inv_h0;
   float margin;      // absolute slack subtracted from every "covered radius" (fp32 rounding of keys)
-  int base_level;    // finest level present in the hash
+  int base_level;    // search level of the correspondence / public k-NN searches: finest level with mean occupancy >= 2
   unsigned int level_hist[16];  // level_hist[d] = #sorted positions whose key first differs from the
                                 // predecessor at level d-1 (d = 13: differs at the top / first point)
   unsigned int cells_total;     // entries inserted into the hash
-  unsigned int pad[3];
+  int fine_level;               // finest level present in the hash (<= base_level): as fine as the table has room for; only
+                                // the leaf-scheduled self k-NN (lknn.cuh) goes below base_level, where the cloud is dense
+  unsigned int pad[2];
 };
 
 // Read-only view handed to the kernels by value.

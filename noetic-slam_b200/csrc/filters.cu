@@ -24,6 +24,7 @@
 namespace ngicp {
 
 int upload_points(Handle* h, const void* points, size_t n, size_t stride_bytes, float** d_xyz, int* stride_floats);   // api.cu
+int finish_input_copy(Handle* h);                                                                                     // api.cu
 
 namespace {
 
@@ -497,7 +498,8 @@ int ngicp_filter_scan(ngicp_handle* p, const void* points, size_t n, size_t stri
   }
   *n_out = cur_n;
   dev_free(d_in, s); dev_free(d_crop, s); dev_free(d_vox, s);
-  return rc;
+  const int rc2 = finish_input_copy(h);
+  return rc ? rc : rc2;
 }
 
 int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stride_bytes, size_t time_offset_bytes, int time_type,

@@ -106,6 +106,7 @@ __device__ __forceinline__ void write_meta(GridMeta* meta, float h0) {
   meta->inv_h0 = 1.0f / h0;                   // exact: power of two
   meta->margin = h0 * (1.0f / 512.0f);
   meta->base_level = 0;
+  meta->fine_level = 0;
   meta->cells_total = 0;
   for (int i = 0; i < 16; i++) meta->level_hist[i] = 0;
 }
@@ -199,11 +200,11 @@ __global__ void __launch_bounds__(256) gather_levels_kernel(const float* __restr
   if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&meta->level_hist[threadIdx.x], h[threadIdx.x]);
 }
 
-// cells(L) = #positions with diff_levels > L. Base level = finest level whose mean occupancy is
-// >= occupancy and whose cumulative entry count (this level and all coarser ones) fits the table.
-// The keys are only sorted down to level kSortLevel (finer bits stay in input order inside a cell), so cells are
-// contiguous ranges for levels >= kSortLevel and the base level is never finer than that.
-__device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned int max_entries, int occupancy, unsigned int* total_out) {
+// cells(L) = #positions with diff_levels > L. Base level = finest level whose mean occupancy is >= occupancy and whose
+// cumulative entry count (this level and all coarser ones) fits the table. Fine level = as many finer levels below the
+// base level as still fit the table and still merge points (mean occupancy >= 1.11): a LiDAR scan is two orders of
+// magnitude denser next to the sensor than its mean, and there the self k-NN wants cells finer than the base level.
+__device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned int max_entries, int occupancy, bool want_fine, unsigned int* total_out, int* fine_out) {
   unsigned int cells[kNumLevels];
   unsigned int acc = 0;
   for (int L = kTopLevel; L >= 0; L--) {
@@ -218,7 +219,15 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
     total += cells[L];
     base = L;
   }
+  int fine = base;
+  for (int L = base - 1; want_fine && L >= kSortLevel; L--) {
+    if ((unsigned long long)cells[L] * 10ull > (unsigned long long)n * 9ull) break;
+    if (total + cells[L] > max_entries) break;
+    total += cells[L];
+    fine = L;
+  }
   if (total_out) *total_out = total;
+  if (fine_out) *fine_out = fine;
   return base;
 }
 
@@ -226,17 +235,19 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
 // the cell's slot by find-or-insert (atomicCAS on the key), so one pass over the sorted keys fills start AND end:
 // whichever of the two threads arrives first claims the slot, the fields they write are disjoint.
 __global__ void __launch_bounds__(256) table_build_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta,
-                                                          CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy) {
-  __shared__ int s_base;
+                                                          CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy, bool want_fine) {
+  __shared__ int s_fine;
   if (threadIdx.x == 0) {
     unsigned int total;
-    s_base = choose_base(meta, n, max_entries, occupancy, &total);
-    if (blockIdx.x == 0) { meta->base_level = s_base; meta->cells_total = total; }   // published for every later kernel
+    int fine;
+    const int b = choose_base(meta, n, max_entries, occupancy, want_fine, &total, &fine);
+    s_fine = fine;
+    if (blockIdx.x == 0) { meta->base_level = b; meta->fine_level = fine; meta->cells_total = total; }   // published for every later kernel
   }
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const int base = s_base;
+  const int base = s_fine;
   const unsigned long long k = keys[j];
   const int d_open = j == 0 ? kNumLevels : diff_levels(k, keys[j - 1]);
   const int d_close = j == n - 1 ? kNumLevels : diff_levels(k, keys[j + 1]);
@@ -260,11 +271,14 @@ inline int ceil_log2(unsigned int v) { int b = 0; while ((1u << b) < v) b++; ret
 
 void free_index(Index* idx, cudaStream_t stream) {
   if (!idx) return;
+  // the freeing stream may not be the one that built (or last adopted) the index: order the free after the build
+  order_after_build(idx, stream);
   dev_free(idx->arena, stream);
+  if (idx->built) cudaEventDestroy(idx->built);
   delete idx;
 }
 
-int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t* seg_offsets, int n_seg, Index** out) {
+int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t* seg_offsets, int n_seg, Index** out, bool fine) {
   if (n <= 0) return fail(h, NGICP_ERR_INVALID, "index build: empty cloud");
   if (n_seg < 1 || n_seg > (1 << kMaxSegBits)) return fail(h, NGICP_ERR_INVALID, "index build: bad segment count");
   if ((long long)n >= (1ll << 31) - 4096) return fail(h, NGICP_ERR_UNSUPPORTED, "index build: more than 2^31 points");
@@ -289,7 +303,8 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   const int nbits = kMortonBits - low_bit + (n_seg > 1 ? ceil_log2((unsigned)n_seg) : 0);
   const int passes = sort_num_passes(nbits);
   unsigned int cap = 1024;
-  while (cap < (unsigned long long)n + n / 2) cap <<= 1;
+  // 24-48 B of table per point; with the fine levels (choose_base) 64-128 B
+  while (cap < (fine ? 4ull * (unsigned long long)n : (unsigned long long)n + n / 2)) cap <<= 1;
   idx->table_mask = cap - 1;
 
   // two stream-ordered allocations per build: the index's own arena and one scratch block
@@ -356,9 +371,12 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
     keys_sorted = idx->keys;
   }
   gather_levels_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, keys_sorted, idx->pts, idx->inv, idx->meta);
-  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, cap / 2, 2);
+  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, fine ? cap / 2 + cap / 8 : cap / 2, 2, fine);
   count_launch(h, 2);
   IDX_CUDA(cudaGetLastError());
+  IDX_CUDA(cudaEventCreateWithFlags(&idx->built, cudaEventDisableTiming));
+  IDX_CUDA(cudaEventRecord(idx->built, s));
+  idx->built_stream = s;
   dev_free(scratch, s);
 #undef IDX_CUDA
   *out = idx;

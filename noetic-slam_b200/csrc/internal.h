@@ -42,6 +42,11 @@ struct ngicp_index {
   float4* seg_origin = nullptr;           // [n_seg]
   int* seg_start = nullptr;               // [n_seg+1]
   std::vector<int64_t> seg_offsets_host;  // [n_seg+1]
+  // recorded at the end of the build on the building handle's stream: any OTHER stream that touches the index
+  // (a handle that adopts or queries it) waits on it first — DLIO builds the submap tree on one NanoGICP object and
+  // hands it to another (odom.cc:1737-1738 -> :995)
+  cudaEvent_t built = nullptr;
+  cudaStream_t built_stream = nullptr;
   ngicp::GridView view() const {
     ngicp::GridView g;
     g.pts = pts; g.inv = inv; g.table = table; g.meta = meta; g.seg_origin = seg_origin; g.seg_start = seg_start;
@@ -86,12 +91,20 @@ struct ngicp_handle {
   void* stage_host = nullptr;
   size_t stage_cap = 0;
   cudaEvent_t stage_done = nullptr;  // last H2D out of stage_host
+  // page-locked caller clouds are copied straight out of the caller's buffer (api.cu:upload_xyz): by default the entry
+  // point returns only after that copy has landed; ngicp_set_async_input(h, 1) lets it return while the copy is in flight
+  bool async_input = false;
+  bool input_pending = false;
+  cudaEvent_t input_copied = nullptr;
   double* batch_partials = nullptr;  // batched reductions (allocated on first use)
   size_t batch_partials_cap = 0;
   // tuning knobs (env NGICP_K4_CMAX / NGICP_K2_CMAX_MULT override)
   int k4_cmax = 64;
   int k2_cmax_mult = 4;
   int k2_lpq = 0;   // lanes per query in K2 (0 = pick by cloud size)
+  int k2_leaf = 1;  // leaf-scheduled K2 (lknn.cuh); NGICP_K2_LEAF=0 = the warp-cooperative search of round 1
+  int k2_chunk = 256;              // staging chunk of the leaf search (128 or 256)
+  unsigned int* k2_ctr = nullptr;  // [4] item count / next item / finished warps of the leaf search (zero between calls)
   int k4_lpq = 0;
   int k4_ball = 1;  // seed re-association with the previous correspondences (NGICP_K4_BALL=0 disables)
   // LM state (lsq_registration.h:151-168)
@@ -122,8 +135,15 @@ int fail(Handle* h, int code, const std::string& msg);
 
 // ---- stage entry points (each in its own .cu) --------------------------------------------------
 // K1. xyz: device array of n points, `stride_floats` (3 or 4) floats apart.
-int build_index(Handle* h, const float* d_xyz, int stride_floats, int n, const int64_t* seg_offsets, int n_seg, Index** out);
+// fine: also insert the levels below the base level the table has room for (lknn.cuh needs them where a scan is dense).
+// Clouds that are only ever searched INTO (the submap target: covariances come from its keyframes) are built without.
+int build_index(Handle* h, const float* d_xyz, int stride_floats, int n, const int64_t* seg_offsets, int n_seg, Index** out, bool fine = true);
 void free_index(Index* idx, cudaStream_t stream);
+// make `stream` wait for the build of idx unless it IS the building stream (no-op then)
+inline cudaError_t order_after_build(const Index* idx, cudaStream_t stream) {
+  if (!idx || !idx->built || idx->built_stream == stream) return cudaSuccess;
+  return cudaStreamWaitEvent(stream, idx->built, 0);
+}
 // K2. self k-NN of every indexed point, as sorted positions. Layout of the table (transient between K2 and K3):
 // k = 16 / 20 (the compile-time paths of K3): TILED — points in tiles of 32, chunk c (int4 = neighbours 4c..4c+3) of
 // the 32 points of a tile contiguous: int4 index ((j / 32) * (k / 4) + c) * 32 + j % 32, so that both K2's writes and
@@ -132,6 +152,7 @@ inline bool nbr_tiled(int k) { return k == 16 || k == 20; }
 inline size_t nbr_elems(size_t n, int k) { return ((n + 31) / 32) * 32 * (size_t)k; }
 // dens_term[n] (optional) = sum_{j>=1} d2_j / normalization, the per-point density term.
 int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term);
+int export_self_rows(Handle* h, const Index* idx, const int* d_nbr, int k, int* d_out);   // knn.cu: K2's table as original-index rows
 // public k-NN: queries on device (float4), results in ORIGINAL indices, canonical order
 int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, int* d_out_idx, float* d_out_sqd);
 // K3. covariance + regularisation from the k-NN table

@@ -159,7 +159,7 @@ int ngicp_submap_assemble(ngicp_handle* h, ngicp_keyframe* const* kfs, int n_kfs
     off += kfs[i]->n;
   }
   Index* idx = nullptr;
-  int rc = build_index(h, reinterpret_cast<const float*>(d_pts), 4, (int)n, nullptr, 1, &idx);
+  int rc = build_index(h, reinterpret_cast<const float*>(d_pts), 4, (int)n, nullptr, 1, &idx, n <= 262144);   // submaps: no fine levels (covariances are the keyframes')
   dev_free(d_pts, s);
   if (rc) { dev_free(d_cov, s); return rc; }
   rc = swap_in_index(h, NGICP_TARGET, idx);   // drops the old target covariances, like setInputTarget

@@ -7,6 +7,7 @@
 // ordered by (distance, original index).
 #include "internal.h"
 #include "wknn.cuh"
+#include "lknn.cuh"
 
 namespace ngicp {
 
@@ -114,6 +115,86 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
   }
 }
 
+
+// ---- leaf-scheduled K2 (lknn.cuh) ---------------------------------------------------------------------------------
+// Work items of the search: one thread per sorted position; the heads of the finest grouping cells (level base+1) climb
+// to their leaf = the largest ancestor with <= cmax points (the finest grouping cell itself if even that holds more) and
+// the first point of a leaf appends ceil(members / 32) items. ctr[0] = number of items.
+__global__ void __launch_bounds__(256) leaf_items_kernel(GridView g, const unsigned long long* __restrict__ keys, int cmax,
+                                                         LeafItem* __restrict__ items, unsigned int* __restrict__ ctr) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n) return;
+  const int base = __ldg(&g.meta->fine_level);     // the finest level in the table
+  const unsigned long long key = __ldg(keys + j);
+  const int sh = 3 * (base + 1);
+  if (j > 0 && (__ldg(keys + j - 1) >> sh) == (key >> sh)) return;      // not the first point of its finest grouping cell
+  int P = min(base + 1, kTopLevel);
+  uint32_t s = 0, e = 0;
+  if (!cell_lookup(g.table, g.table_mask, cell_key(key, P), s, e)) return;   // cannot happen: every cell >= base is in the table
+  while (P < kTopLevel) {
+    uint32_t s2, e2;
+    if (!cell_lookup(g.table, g.table_mask, cell_key(key, P + 1), s2, e2) || (int)(e2 - s2) > cmax) break;
+    P++; s = s2; e = e2;
+  }
+  if ((int)s != j) return;                                                // the leaf belongs to its first point
+  const int mcount = (int)(e - s), nit = (mcount + 31) / 32;
+  const unsigned int at = atomicAdd(&ctr[0], (unsigned int)nit);
+  for (int c = 0; c < nit; c++) {
+    LeafItem it;
+    it.start = (int)s + 32 * c;
+    it.count_level = (min(32, mcount - 32 * c) << 8) | P;
+    it.pre = max((int)s, min(it.start, (int)e - 32));
+    it.pre_count = min(32, (int)e - it.pre);
+    items[at + c] = it;
+  }
+}
+
+constexpr int kLeafWarps = 4;
+// Persistent warps: every warp draws items from ctr[1] until the list is exhausted; the last warp to leave resets the
+// three counters, so the next k-NN call on this handle finds them zero without a memset.
+template <int KP, int KC, int C>
+__global__ void __launch_bounds__(32 * kLeafWarps) knn_leaf_kernel(GridView g, int k_rt, const LeafItem* __restrict__ items, unsigned int* __restrict__ ctr,
+                                                                   int normalization, bool tiled, int* __restrict__ nbr, double* __restrict__ dens_term) {
+  extern __shared__ __align__(16) unsigned char leaf_smem[];     // kLeafWarps x LeafScratch (dynamic: the big lists exceed 48 KB)
+  LeafScratch<KP, C>& ws = reinterpret_cast<LeafScratch<KP, C>*>(leaf_smem)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int k = KC > 0 ? KC : k_rt;
+  if (lane == 0) { mbar_init(&ws.mbar[0], 1); mbar_init(&ws.mbar[1], 1); }
+#pragma unroll
+  for (int i = 0; i < kLeafPend; i++) ws.pend[i][lane] = __int_as_float(0x7f800000);
+  __syncwarp();
+  uint32_t phase = 0u;
+  const unsigned int n_items = *reinterpret_cast<volatile unsigned int*>(&ctr[0]);
+  for (;;) {
+    unsigned int it = 0;
+    if (lane == 0) it = atomicAdd(&ctr[1], 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_items) break;
+    const LeafItem item = items[it];
+    leaf_knn_item<KP, KC, C>(g, item, k_rt, ws, phase, [&](int j, int (&a)[KP < 16 ? 16 : KP], double dsum) {
+      sort_ascending(a);
+      if (KC > 0 && (KC % 4) == 0 && tiled) {
+#pragma unroll
+        for (int c = 0; c < KC / 4; c++) {
+          const int4 v = c == 0 ? make_int4(j, a[0], a[1], a[2]) : make_int4(a[4 * c - 1], a[4 * c], a[4 * c + 1], a[4 * c + 2]);
+          *nbr_chunk<KC>(nbr, j, c, true) = v;
+        }
+      } else {
+        int* row = nbr + (size_t)j * k;
+        row[0] = j;
+#pragma unroll
+        for (int i = 0; i + 1 < KP; i++) if (i + 1 < k) row[i + 1] = a[i];
+      }
+      if (dens_term) dens_term[j] = dsum / (double)normalization;
+    });
+  }
+  if (lane == 0) {
+    __threadfence();
+    const unsigned int total = gridDim.x * kLeafWarps;
+    if (atomicAdd(&ctr[2], 1u) == total - 1u) { ctr[0] = 0u; ctr[1] = 0u; __threadfence(); ctr[2] = 0u; }
+  }
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(64) knn_self_dyn_kernel(GridView g, int k, int start_count, int normalization,
                                                          int* __restrict__ nbr, double* __restrict__ dens_term) {
@@ -173,6 +254,19 @@ __global__ void __launch_bounds__(64) knn_query_dyn_kernel(GridView g, const flo
   write_public(g, best, k, k, out_idx + (size_t)i * k, out_sqd + (size_t)i * k);
 }
 
+constexpr int kMaxK = 128;
+// inspection export (ngicp_self_neighbours): K2's table (sorted positions, tiled or row-major) -> rows of ORIGINAL indices in
+// original point order; entry 0 of a row is the point itself
+__global__ void __launch_bounds__(256) export_self_rows_kernel(GridView g, const int* __restrict__ nbr, int k, bool tiled, int* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n) return;
+  const int orig = __float_as_int(__ldg(&g.pts[j].w));
+  for (int i = 0; i < k; i++) {
+    const int pos = tiled ? nbr[(((size_t)(j >> 5) * (k / 4) + (i >> 2)) * 32 + (j & 31)) * 4 + (i & 3)] : nbr[(size_t)j * k + i];
+    out[(size_t)orig * k + i] = (pos >= 0 && pos < g.n) ? __float_as_int(__ldg(&g.pts[pos].w)) : -1;
+  }
+}
+
 inline int start_count_for(int k) { return k < 4 ? 1 : (k + 3) / 4; }
 // group-cell capacity of the warp-cooperative search: large enough that the k-th neighbour of a member
 // lies inside the staged block (block reach >= half the group cell), small enough to keep the scan short
@@ -180,7 +274,25 @@ inline int group_cap_for(int k, int mult) { return k * mult > 32 ? k * mult : 32
 
 }  // namespace
 
-constexpr int kMaxK = 128;
+
+// persistent grid of the leaf search: as many CTAs as the device holds at once (queried once per instantiation)
+template <int KP, int KC, int C>
+static int launch_leaf_search(Handle* h, const Index* idx, int k, int normalization, const LeafItem* items, int* d_nbr, double* d_dens_term) {
+  static int per_sm = 0;
+  constexpr size_t smem = sizeof(LeafScratch<KP, C>) * kLeafWarps;
+  if (per_sm == 0) {
+    int v = 0;
+    NGICP_CUDA(h, cudaFuncSetAttribute(knn_leaf_kernel<KP, KC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NGICP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, knn_leaf_kernel<KP, KC, C>, 32 * kLeafWarps, smem));
+    per_sm = v > 0 ? v : 1;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int want = (idx->n / 16) / kLeafWarps + 1;     // an item is ~23 points on average
+  const int grid = std::max(1, std::min(sms * per_sm, want));
+  knn_leaf_kernel<KP, KC, C><<<grid, 32 * kLeafWarps, smem, h->stream>>>(idx->view(), k, items, h->k2_ctr, normalization, nbr_tiled(k), d_nbr, d_dens_term);
+  return NGICP_OK;
+}
 
 int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term) {
   if (k < 1 || k > kMaxK) return fail(h, NGICP_ERR_UNSUPPORTED, "k must be in [1,128]");
@@ -189,6 +301,30 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   const int normalization = ((k - 1) * (2 + k)) / 2;  // integer arithmetic, nano_gicp.cc:345
   const int sc = start_count_for(k);
   cudaStream_t s = h->stream;
+  if (k <= 32 && h->k2_leaf) {
+    // leaf-scheduled search (lknn.cuh): work items first, then the persistent search over them
+    if (!h->k2_ctr) {
+      NGICP_CUDA(h, cudaMalloc(&h->k2_ctr, sizeof(unsigned int) * 4));
+      NGICP_CUDA(h, cudaMemsetAsync(h->k2_ctr, 0, sizeof(unsigned int) * 4, s));
+    }
+    LeafItem* items = nullptr;
+    NGICP_CUDA(h, dev_alloc(&items, (size_t)n + (size_t)n / 32 + 1, s));
+    leaf_items_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, idx->keys, group_cap_for(k, h->k2_cmax_mult), items, h->k2_ctr);
+    int rc;
+#define LEAF(KP, KC) (h->k2_chunk == 128 ? launch_leaf_search<KP, KC, 128>(h, idx, k, normalization, items, d_nbr, d_dens_term) \
+                                         : launch_leaf_search<KP, KC, 256>(h, idx, k, normalization, items, d_nbr, d_dens_term))
+    if (k == 16) rc = LEAF(16, 16);
+    else if (k == 20) rc = LEAF(32, 20);
+    else if (k <= 8) rc = LEAF(8, 0);
+    else if (k <= 16) rc = LEAF(16, 0);
+    else rc = LEAF(32, 0);
+#undef LEAF
+    dev_free(items, s);
+    if (rc) return rc;
+    count_launch(h, 2);
+    NGICP_CUDA(h, cudaGetLastError());
+    return NGICP_OK;
+  }
   // lanes per query: small clouds need the extra warps, big ones prefer the sharing of one query per lane
   const int lpq = h->k2_lpq > 0 ? h->k2_lpq : (n < 1500000 ? 4 : 1);
 #define LAUNCH_SELF_L(K, LPQ)                                                                                             \
@@ -203,6 +339,13 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   else knn_self_dyn_kernel<kMaxK><<<(n + 63) / 64, 64, 0, s>>>(g, k, sc, normalization, d_nbr, d_dens_term);
 #undef LAUNCH_SELF
 #undef LAUNCH_SELF_L
+  count_launch(h);
+  NGICP_CUDA(h, cudaGetLastError());
+  return NGICP_OK;
+}
+
+int export_self_rows(Handle* h, const Index* idx, const int* d_nbr, int k, int* d_out) {
+  export_self_rows_kernel<<<(idx->n + 255) / 256, 256, 0, h->stream>>>(idx->view(), d_nbr, k, nbr_tiled(k), d_out);
   count_launch(h);
   NGICP_CUDA(h, cudaGetLastError());
   return NGICP_OK;

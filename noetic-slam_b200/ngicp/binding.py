@@ -21,8 +21,8 @@ SOURCE, TARGET = 0, 1
 # every symbol include/ngicp_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "ngicp_default_params", "ngicp_version", "ngicp_last_error", "ngicp_create", "ngicp_destroy", "ngicp_set_params",
-    "ngicp_get_params", "ngicp_stream", "ngicp_synchronize", "ngicp_index_build", "ngicp_index_build_device",
-    "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_index_keys", "ngicp_set_input", "ngicp_set_input_device",
+    "ngicp_get_params", "ngicp_set_async_input", "ngicp_stream", "ngicp_synchronize", "ngicp_index_build", "ngicp_index_build_device",
+    "ngicp_index_retain", "ngicp_index_release", "ngicp_index_size", "ngicp_knn", "ngicp_self_neighbours", "ngicp_index_keys", "ngicp_set_input", "ngicp_set_input_device",
     "ngicp_attach_index", "ngicp_get_index", "ngicp_swap_source_and_target", "ngicp_clear", "ngicp_compute_covariances",
     "ngicp_get_covariances", "ngicp_set_covariances", "ngicp_has_covariances", "ngicp_update_correspondences",
     "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances", "ngicp_set_input_batch", "ngicp_batch_linearize",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.ngicp_destroy.argtypes = [vp]
     L.ngicp_set_params.argtypes = [vp, C.POINTER(Params)]
     L.ngicp_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.ngicp_set_async_input.argtypes = [vp, i]
     L.ngicp_stream.restype = vp
     L.ngicp_stream.argtypes = [vp]
     L.ngicp_synchronize.argtypes = [vp]
@@ -90,6 +91,7 @@ def lib() -> C.CDLL:
     L.ngicp_index_size.restype = sz
     L.ngicp_index_size.argtypes = [vp]
     L.ngicp_knn.argtypes = [vp, vp, vp, sz, sz, i, ip, fp]
+    L.ngicp_self_neighbours.argtypes = [vp, i, i, ip, dp]
     L.ngicp_index_keys.argtypes = [vp, vp, C.POINTER(C.c_uint64), fp]
     L.ngicp_set_input.argtypes = [vp, i, vp, sz, sz]
     L.ngicp_set_input_device.argtypes = [vp, i, vp, sz]

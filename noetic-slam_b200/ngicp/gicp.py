@@ -276,6 +276,17 @@ class NanoGICP:
         self.target_density_ = self._calc(B.TARGET)
         return True
 
+    def selfNeighbours(self, which=B.SOURCE, k=None):
+        """Inspection: the neighbour sets calculate_covariances works on (nano_gicp.cc:343), from the production K2 search.
+        -> (idx (N,k) int32 original indices, row i = [i, its other k-1 nearest in unspecified order], density terms (N,))."""
+        tree = self.source_kdtree_ if which == B.SOURCE else self.target_kdtree_
+        n = tree.size()
+        k = int(k or self.k_correspondences_)
+        idx = np.empty((n, k), np.int32)
+        dens = np.empty(n, np.float64)
+        B.check(self._h, self._L.ngicp_self_neighbours(self._h, which, k, _ptr(idx, C.c_int), _ptr(dens, C.c_double)))
+        return idx, dens
+
     def _get_covs(self, which):
         n = C.c_size_t(0)
         if not self._L.ngicp_has_covariances(self._h, which, C.byref(n)):

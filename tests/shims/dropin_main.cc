@@ -14,7 +14,7 @@ struct Point {  // layout of dlio::Point (src/dlio/include/dlio/dlio.h:85-108): 
 static_assert(sizeof(Point) == 32, "dlio::Point is 32 bytes");
 
 static pcl::PointCloud<Point>::Ptr load(const char* path) {
-  auto c = std::make_shared<pcl::PointCloud<Point>>();
+  pcl::PointCloud<Point>::Ptr c(new pcl::PointCloud<Point>);   // boost::shared_ptr with PCL <= 1.10, std::shared_ptr from 1.11
   FILE* f = std::fopen(path, "rb");
   if (!f) { std::perror(path); std::exit(2); }
   float v[3];
