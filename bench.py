@@ -15,8 +15,12 @@ covariance) + align (K4 linearise / K5 error per LM iteration, 6x6 solve on the 
           pose out): pack + H2D + kernels + D2H inside the timed region (wall clock around the
           synchronous call).
 N > 1 (torchrun, one rank per GPU): every rank registers its own sequence against its own submap
-(BASELINE config 5 shape; no data-path collective) — weak scaling, value = total scans/s over the
-max-over-ranks time.
+(no data-path collective) — weak scaling, value = total scans/s over the max-over-ranks time.
+Beside the headline the line carries the BASELINE configs that shard (strong scaling, fixed total work):
+  bulk.all_ranks       cfg 3: 256 keyframes x 65,536 points = 16,777,216 points, keyframe i -> rank i mod N
+  multi_sequence_8     cfg 5: 8 seeded MulRan-shaped sequences through the odom loop, sequence i -> rank i mod N
+and, on rank 0 at N = 1, cfg 4: a 500-scan OS1-64 trajectory through the odom loop over the CUDA path and over the
+CPU oracle with their scan-by-scan agreement counters.
 --impl reference: the CPU oracle (reference nanoflann.h + restated nano_gicp, OpenMP on all host
 cores) on the same workload; rank 0 only.
 """
@@ -41,6 +45,10 @@ N_SUBMAP = 1_000_000
 N_KEYFRAMES = 40
 N_DISTINCT_SCANS = 8
 K_CORR = 16
+CFG3_KEYFRAMES = 256          # BASELINE config 3: 256 x 65,536 = 16,777,216 points, sharded by keyframe
+CFG5_SEQUENCES = 8            # BASELINE config 5
+CFG5_SCANS = int(os.environ.get("NGICP_BENCH_CFG5_SCANS", 200))
+CFG4_SCANS = int(os.environ.get("NGICP_BENCH_CFG4_SCANS", 500))
 # algorithmic bytes per unit: compulsory traffic only
 BYTES = {
     "K1_index_per_pt": 36,        # 16 R + 16 W reordered float4 + 4 W permutation
@@ -182,19 +190,72 @@ def workload_config(world):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def pin_rank_to_cores(local_rank, world):
+    """Disjoint host cores per rank: the LM loop is ~12 launch -> poll round trips per scan, and eight unpinned processes
+    (plus a clock sampler) on the same cores turn into step-time jitter at N = 8."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
+
+
+def dropin_cpp_e2e(tgt, bounds, scans, steps, warmup):
+    """The C++ drop-in surface (include/nano_gicp/nano_gicp.h) driven the way dlio::OdomNode drives the reference, on fresh
+    pageable pcl::PointCloud scans: tests/shims/dropin_bench.cc compiled here against the PCL/Eigen shims (PCL is absent)."""
+    import tempfile
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    lib = ROOT / "noetic-slam_b200" / "libngicp_b200.so"
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        exe = Path(td) / "dropin_bench"
+        cmd = [cxx, "-std=c++17", "-O2", "-DSHIM_PCL_MINOR=10", f"-I{ROOT / 'tests' / 'shims'}", f"-I{ROOT / 'include'}",
+               str(ROOT / "tests" / "shims" / "dropin_bench.cc"), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"error": "compile failed: " + r.stderr[-300:]}
+        np.ascontiguousarray(tgt, np.float32).tofile(Path(td) / "tgt.bin")
+        np.ascontiguousarray(bounds, np.int64).tofile(Path(td) / "bounds.bin")
+        names = []
+        for i, sc in enumerate(scans):
+            np.ascontiguousarray(sc, np.float32).tofile(Path(td) / f"scan{i}.bin")
+            names.append(str(Path(td) / f"scan{i}.bin"))
+        for key, flag in (("align_fills_output_cloud", "1"), ("output_cloud_skipped", "0")):
+            r = subprocess.run([str(exe), str(Path(td) / "tgt.bin"), str(Path(td) / "bounds.bin"), str(steps), str(warmup), flag] + names,
+                               capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                out[key] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            out[key] = json.loads(r.stdout.strip().splitlines()[-1])
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import ngicp
     from ngicp import sharding, synth
 
+    cores = pin_rank_to_cores(local_rank, world)
+    # ---- host data first: the sequence generators fork worker processes, which must happen before CUDA is initialised
+    t_gen = time.time()
+    tgt, bounds, scans = make_workload(rank)
+    owned_seq = sharding.units_for_rank(CFG5_SEQUENCES, rank, world)
+    specs = [(100 + k, CFG5_SCANS, 0.4, 1, True) for k in owned_seq]          # cfg 5: MulRan-shaped (t = 0), one deskew group
+    with_cfg4 = world == 1 and CFG4_SCANS > 0
+    if with_cfg4:
+        specs.append((4, CFG4_SCANS, 0.4, 2, False))                           # cfg 4: OS1-64 time stamps, sensor moving during the scan
+    seqs = generate_sequences(specs, world) if (CFG5_SCANS > 0 or with_cfg4) else []
+    seq_cfg4 = seqs.pop() if with_cfg4 else None
+    log(f"[rank {rank}] workload + {len(specs)} sequences generated in {time.time() - t_gen:.1f}s (cores {cores[:1]}..{cores[-1:] if cores else ''})")
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    t_gen = time.time()
-    tgt, bounds, scans = make_workload(rank)
-    log(f"[rank {rank}] workload generated in {time.time() - t_gen:.1f}s")
 
     g = configure(ngicp.NanoGICP(local_rank))
     # submap resident in HBM: per-keyframe covariances in ONE batched pass (reuse), then the 1M-pt index
@@ -225,16 +286,20 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_job(t, u):
+        return sharding.reduce_job(t, u, device=dev)
+
     W, K = max(3, args.warmup), args.steps     # never fewer than three warm-up steps (timing rules)
     # ---- value: device-resident input, CUDA events on the handle's stream
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # one sampler per job, not one per rank
     iters = []
     g.timings(reset=True)
     launches0 = 0
     dts = []
     for i in range(W + K):
         if i == W:
-            sampler.start()
+            if sampler:
+                sampler.start()
             barrier()
             launches0 = g.timings(reset=False)["kernel_launches"]
         flush_l2()
@@ -251,36 +316,60 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     launches = g.timings(reset=False)["kernel_launches"] - launches0
     t_local = float(sum(dts[W:]))
-    t_max, units = sharding.reduce_job(t_local, float(K), device=dev)
+    t_max, units = reduce_job(t_local, float(K))
     value = units / t_max
+    # per-rank spread of the step time (separates jitter from a systematic slow-down at N > 1)
+    step_ms = [1e3 * float(np.median(dts[W:])), 1e3 * float(np.min(dts[W:])), 1e3 * float(np.max(dts[W:]))]
+    if world > 1:
+        allv = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+        allv[rank] = torch.tensor(step_ms, dtype=torch.float64)
+        dist.all_reduce(allv)
+        per_rank = allv.cpu().numpy().tolist()
+    else:
+        per_rank = [step_ms]
 
-    # ---- e2e: host buffers through the reference-facing API, wall clock
-    e2e_ts = []
-    for i in range(W + K):
-        if i == W:
-            barrier()
-        flush_l2()
-        hs = pinned[i % len(pinned)].numpy()           # page-locked 32-byte AoS scan buffer (a registered PCL cloud), refilled
-        hs[:] = h_scans[i % len(h_scans)]              # outside the timed region; align() below has synchronised its last use
-        t0 = time.perf_counter()
-        g.setInputSource(hs)
-        g.calculateSourceCovariances()
-        T = g.align()
-        e2e_ts.append(time.perf_counter() - t0)
-    barrier()
-    clocks = sampler.stop()     # sampled across both timed regions (device-resident loop and host-buffer loop)
-    e_max, e_units = sharding.reduce_job(float(sum(e2e_ts[W:])), float(K), device=dev)
-    e2e_value = e_units / e_max
+    # ---- e2e: host buffers through the reference-facing API, wall clock. Two kinds of scan buffer:
+    #      page-locked (a registered cloud: copied as it is) and pageable (what an unmodified DLIO hands over: a fresh
+    #      pcl::PointCloud per scan, packed into the handle's pinned staging buffer)
+    def e2e_loop(kind):
+        ts = []
+        for i in range(W + K):
+            if i == W:
+                barrier()
+            flush_l2()
+            if kind == "pinned":
+                hs = pinned[i % len(pinned)].numpy()       # refilled outside the timed region; align() has synchronised its last use
+                hs[:] = h_scans[i % len(h_scans)]
+            else:
+                hs = h_scans[i % len(h_scans)].copy()      # a fresh pageable cloud, just written by the CPU (as a deskewed scan is)
+            t0 = time.perf_counter()
+            g.setInputSource(hs)
+            g.calculateSourceCovariances()
+            g.align()
+            ts.append(time.perf_counter() - t0)
+        barrier()
+        e_max, e_units = reduce_job(float(sum(ts[W:])), float(K))
+        return e_units / e_max, 1e3 * e_max / K
 
-    # ---- BASELINE config 3 across the ranks: every rank builds the covariances of its own 64 keyframes (keyframes never
-    #      interact: sharded by keyframe, no collective); aggregate = points of all ranks / max over ranks of the device time
+    e2e_value, e2e_ms = e2e_loop("pinned")
+    e2e_pg_value, e2e_pg_ms = e2e_loop("pageable")
+    clocks = sampler.stop() if sampler else None     # sampled across the timed regions (device-resident loop and host-buffer loops)
+
+    # ---- BASELINE config 3 across the ranks (strong scaling): 256 keyframes x 65,536 points in total, keyframe i on rank i mod N
     hbm = peak_hbm()
-    bulk = bulk_covariance(g, scans, hbm)
+    owned_kf = sharding.units_for_rank(CFG3_KEYFRAMES, rank, world)
+    bulk = bulk_covariance_cfg3(g, scans, hbm, owned_kf)
     shard_ms = bulk["index_ms"] + bulk["knn_ms"] + bulk["covariance_ms"]
-    b_t, b_pts = sharding.reduce_job(shard_ms * 1e-3, float(bulk["points"]), device=dev)
-    k3_t, _ = sharding.reduce_job(bulk["covariance_ms"] * 1e-3, 0.0, device=dev)
-    bulk["all_ranks"] = {"ranks": world, "points": int(b_pts), "covariance_build_mpts_s": b_pts / b_t / 1e6,
-                         "K3_only_gpts_s": b_pts / k3_t / 1e9, "scaling": "weak (64 keyframes x 65,536 points per GPU)"}
+    b_t, b_pts = reduce_job(shard_ms * 1e-3, float(bulk["points"]))
+    k3_t, _ = reduce_job(bulk["covariance_ms"] * 1e-3, 0.0)
+    k2_t, _ = reduce_job(bulk["knn_ms"] * 1e-3, 0.0)
+    bulk["all_ranks"] = {"ranks": world, "keyframes": CFG3_KEYFRAMES, "points": int(b_pts), "covariance_build_mpts_s": b_pts / b_t / 1e6,
+                         "build_ms_max_over_ranks": 1e3 * b_t, "knn_ms_max_over_ranks": 1e3 * k2_t, "K3_only_gpts_s": b_pts / k3_t / 1e9,
+                         "scaling": "strong (16,777,216 points in total, keyframe i -> rank i mod N)"}
+
+    # ---- BASELINE config 5 across the ranks (strong scaling): 8 sequences through the odom loop
+    multi8 = multi_sequence_cfg5(local_rank, rank, world, seqs, owned_seq, barrier, reduce_job) if CFG5_SCANS > 0 else None
+    del seqs
 
     if rank != 0:
         if world > 1:
@@ -314,49 +403,243 @@ def run_gpu(args, rank, local_rank, world):
     kernels = {k: {"ms_per_launch": ms, "algorithmic_bytes": b, "GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None,
                    "share_of_step": step_share[k] / max(sum(step_share.values()), 1e-9), "ncu_dram_bytes": ncu_traffic(k)} for k, (ms, b) in per.items()}
     dm, db = per[dominant]
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": db / (dm * 1e-3) / 1e9, "peak": hbm["gbs"], "unit": "GB/s",
-                "frac": db / (dm * 1e-3) / 1e9 / hbm["gbs"], "traffic": ncu_traffic(dominant), "peak_source": hbm["source"],
-                "note": "single-scan launches are L2/latency-bound (5 MB per launch); the HBM bar applies to the bulk numbers below"}
+    step_dominant = {"kernel": dominant, "bound": "hbm", "achieved": db / (dm * 1e-3) / 1e9, "peak": hbm["gbs"], "unit": "GB/s",
+                     "frac": db / (dm * 1e-3) / 1e9 / hbm["gbs"], "traffic": ncu_traffic(dominant), "peak_source": hbm["source"],
+                     "note": "single-scan launches are L2/latency-bound (5 MB per launch); the HBM bar applies to the bulk numbers"}
 
-    # ---- judged bulk numbers: K3 on a bulk keyframe batch (BASELINE config 3 shape, bounded to 64 keyframes per GPU)
-    #      and K4b (fused linearisation) on a batch of 64 scans against the resident submap
+    # ---- judged bulk numbers: K3 on the cfg-3 launch above and K4b (fused linearisation) on a batch of 64 scans against the
+    #      resident submap
     bulk.update(bulk_linearize(g, scans, hbm))
     bulk.update(prefilter_probe(g, pinned, h_scans, world == 1))
+    odom4 = None
+    cpp = None
     if world == 1:
         bulk.update(multi_sequence_probe(g, tgt, m4, d_scans, local_rank))
-        bulk.update(odom_loop_probe(local_rank))
+        if seq_cfg4 is not None:
+            odom4 = odom_loop_cfg4(local_rank, seq_cfg4)
+        cpp = dropin_cpp_e2e(tgt, bounds, scans, K, W)
 
     # ---- CPU baseline beside it (bounded sample, all host cores) — rank 0 at N=1 only
     cpu = None
     if world == 1:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))     # the oracle gets every host core
+        except (AttributeError, OSError):
+            pass
         cpu_val, cpu_ms, threads, kind, desc = cpu_register_stream(tgt, bounds, scans, 10, 2)
         cpu = {"value": cpu_val, "unit": "scans/s", "ms_per_step": cpu_ms, "cores": threads, "kind": kind, "sample": desc}
 
-    # Top-level roofline = the covariance kernel (K3) on the bulk keyframe batch: the north star puts the >= 50 % HBM bar on
-    # the covariance and linearisation kernels, and SURVEY.md §8(d) takes K2 (the kernel with the largest share of a single
+    # Top-level roofline = the covariance kernel (K3) on the cfg-3 launch: the north star puts the >= 50 % HBM bar on the
+    # covariance and linearisation kernels, and SURVEY.md §8(d) takes K2 (the kernel with the largest share of a single
     # step, latency/issue-bound exact k-NN) out of the HBM bar. Both judged kernels and the step's dominant kernel are listed.
-    step_dominant = roofline
     roofline = dict(bulk["roofline_K3"])
-    roofline["kernel"] = "K3_covariance, bulk launch (%d keyframes x %d points)" % (bulk["keyframes"], N_SCAN)
+    roofline["kernel"] = "K3_covariance, cfg-3 launch (%d keyframes x %d points on this GPU)" % (bulk["keyframes"], N_SCAN)
     roofline["ms_per_launch"] = bulk["covariance_ms"]
     roofline["judged"] = {"K3_covariance_bulk": bulk["roofline_K3"], "K4b_linearize_batched": bulk["roofline_K4b"]}
     roofline["step_dominant"] = step_dominant
+    mean_it = float(np.mean(iters[W:]))
+    d2h = int(4 + mean_it * (29 * 8 + 8) + 2.5 * mean_it * 16 + 64)   # density + per LM iteration one 29-double result row (+ seq) and ~2.5 error rows + pose
     line = {
         "metric": "gicp_scan_to_submap_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(world),
-        "ms_per_align_step": 1e3 * t_max / K, "lm_iterations_per_scan": float(np.mean(iters[W:])),
-        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": 1e3 * e_max / K, "h2d_bytes_per_step": N_SCAN * 32,
-                "host_buffer": "page-locked 32-byte AoS scan, copied as it is (cudaMemcpyAsync)",
-                "d2h_bytes_per_step": int(8 + np.mean(iters[W:]) * (29 * 8 + 2 * 8) + 64)},
+        "ms_per_align_step": 1e3 * t_max / K, "lm_iterations_per_scan": mean_it,
+        "per_rank_step_ms_median_min_max": per_rank,
+        "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": N_SCAN * 32,
+                "host_buffer": "page-locked 32-byte AoS scan, copied as it is (cudaMemcpyAsync); the call returns when the copy has landed",
+                "d2h_bytes_per_step": d2h, "d2h_note": "host-mapped result rows the kernels write (counted from the row sizes, not metered)"},
+        "e2e_pageable": {"value": e2e_pg_value, "unit": "scans/s", "ms_per_step": e2e_pg_ms, "h2d_bytes_per_step": N_SCAN * 12,
+                         "host_buffer": "fresh pageable 32-byte AoS scan per step (what an unmodified DLIO hands over): xyz packed into the pinned staging "
+                                        "buffer in four slices, each slice's copy overlapping the next slice's packing"},
+        "e2e_cpp_dropin": cpp,
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline, "kernels": kernels, "bulk": bulk,
+        "roofline": roofline, "kernels": kernels, "bulk": bulk, "multi_sequence_8": multi8, "odom_loop_cfg4": odom4,
         "cpu_baseline": cpu,
     }
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- sequences (cfg 4 / cfg 5)
+_SEQ_JOBS = {}   # (seed, step) -> poses; filled before the pool forks
+
+
+def _gen_scan(job):
+    seed, i, step, groups, mulran = job
+    from ngicp import odom, synth
+    return odom.synthetic_scan(synth.Scene(seed), _SEQ_JOBS[(seed, step)], i, seed, 1024, groups, mulran)
+
+
+def generate_sequences(specs, world):
+    """specs: [(seed, n_scans, step_m, deskew_groups, mulran)] -> [list of synthetic_scan tuples]. Ray casting is numpy on
+    the host (0.2-0.5 s per 65,536-point scan), so the scans are made by a fork pool — BEFORE this process touches CUDA."""
+    import multiprocessing as mp
+    from ngicp import odom, synth
+    jobs = []
+    for seed, n, step, groups, mulran in specs:
+        _SEQ_JOBS[(seed, step)] = odom.synthetic_poses(synth.Scene(seed), n, seed, step)
+        jobs += [(seed, i, step, groups, mulran) for i in range(n)]
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    procs = max(1, min(32, cores // max(world, 1)))
+    if procs > 1 and len(jobs) > 8:
+        with mp.get_context("fork").Pool(procs) as pool:
+            flat = pool.map(_gen_scan, jobs, chunksize=4)
+    else:
+        flat = [_gen_scan(j) for j in jobs]
+    out, at = [], 0
+    for seed, n, step, groups, mulran in specs:
+        out.append(flat[at:at + n]); at += n
+    return out
+
+
+def drive_loop(loop, seq, drift, groups, i0, i1, ts=None, res=None):
+    """Scans [i0, i1) of one sequence through an OdomLoop (the prior the IMU integration would supply = the generating pose
+    of every deskew group, disturbed by a seeded drift)."""
+    for i in range(i0, i1):
+        rec, Ts, block, col_t = seq[i]
+        t0 = time.perf_counter()
+        if i == 0:
+            loop.T = Ts[groups // 2].astype(np.float32)
+            loop.propagateGICP()
+            r = loop.callbackPointCloud(rec, None)
+        else:
+            def prior(stamps, Ts=Ts, i=i):
+                k = np.minimum((stamps.astype(np.int64) * groups) // 100_000_000, groups - 1)
+                return (drift[i] @ Ts)[k].astype(np.float32)
+            r = loop.callbackPointCloud(rec, prior)
+        if ts is not None:
+            ts.append(time.perf_counter() - t0)
+        if res is not None:
+            res.append(r)
+
+
+def multi_sequence_cfg5(device, rank, world, seqs, owned, barrier, reduce_job):
+    """BASELINE config 5: 8 independent MulRan-shaped sequences (t = 0: one deskew group, reference
+    src/file_player_mulran/src/ROSThread.cpp:509-518) through the per-scan loop (src/dlio/src/dlio/odom.cc:737-837), sequence i on
+    rank i mod N, the sequences of a rank side by side on its GPU (one handle, stream and host thread each). Strong scaling:
+    the job is the same 8 sequences at every N. Wall clock between barriers (the loop is host-driven), max over ranks."""
+    import ngicp
+    from ngicp import odom, synth
+    warm = 3
+    loops, drifts = [], []
+    for k, seq in zip(owned, seqs):
+        g = configure(ngicp.NanoGICP(device))
+        loops.append(odom.OdomLoop(odom.DeviceBackend(g), odom.OdomParams()))
+        rng = np.random.default_rng(1000 + k)
+        drifts.append([synth.random_se3(rng, 0.03, 0.3) for _ in range(len(seq))])
+    results = [[] for _ in loops]
+    for loop, seq, dr, res in zip(loops, seqs, drifts, results):      # untimed: first scans (allocations, first keyframe, first submap)
+        drive_loop(loop, seq, dr, 1, 0, warm, res=res)
+    gate = threading.Barrier(len(loops) + 1)
+
+    def worker(loop, seq, dr, res):
+        gate.wait()
+        drive_loop(loop, seq, dr, 1, warm, len(seq), res=res)
+        loop.b.gicp.synchronize()
+
+    ths = [threading.Thread(target=worker, args=a) for a in zip(loops, seqs, drifts, results)]
+    for t in ths:
+        t.start()
+    barrier()
+    gate.wait()
+    t0 = time.perf_counter()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    units = float(sum(len(s) - warm for s in seqs))
+    t_max, u_all = reduce_job(dt, units)
+    err = max((float(np.abs(r.T[:3, 3] - s[i][1][0][:3, 3]).max()) for s, res in zip(seqs, results) for i, r in enumerate(res) if r is not None and i > 0), default=0.0)
+    its = [r.iterations + 1 for res in results for r in res[1:] if r is not None]
+    e_max, _ = reduce_job(err, 0.0)
+    return {"sequences": CFG5_SEQUENCES, "scans_per_sequence": len(seqs[0]) if seqs else 0, "timed_scans_all_ranks": int(u_all), "ranks": world,
+            "sequences_on_this_rank": len(seqs), "scans_per_s": u_all / t_max, "wall_s_max_over_ranks": t_max, "scaling": "strong (8 sequences in total)",
+            "keyframes_rank0": [len(l.keyframes) for l in loops], "lm_iterations_mean_rank0": float(np.mean(its)) if its else None,
+            "max_abs_position_error_m": e_max,
+            "note": "MulRan-shaped 65,536-point records (t = 0), full per-scan loop (ingest, deskew, VoxelGrid, index, covariances, align, keyframes, "
+                    "submap rebuilds); host policy is Python, H2D of the raw records and D2H of the deskewed cloud included"}
+
+
+def odom_loop_cfg4(device, seq, groups=2):
+    """BASELINE config 4 (bounded to CFG4_SCANS scans): a seeded OS1-64 trajectory at 10 Hz, the sensor moving during every scan,
+    through the odom loop over the CUDA path and — the checker and the CPU baseline of this config — over the oracle, with
+    their scan-by-scan agreement (keyframe decisions, submap sets, LM iteration counts, poses)."""
+    import ngicp
+    import oracle
+    from ngicp import odom, synth
+    from odom_backends import OracleBackend
+    import scipy.spatial  # noqa: F401  (one-off import kept out of the per-scan times)
+    n = len(seq)
+    rng = np.random.default_rng(8)
+    drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
+
+    def run(backend):
+        loop = odom.OdomLoop(backend, odom.OdomParams())
+        ts, res = [], []
+        drive_loop(loop, seq, drift, groups, 0, n, ts, res)
+        return loop, res, ts
+
+    lg, rg, tg = run(odom.DeviceBackend(configure(ngicp.NanoGICP(device))))
+    threads = os.cpu_count() or 1
+    variant = "ref" if oracle.available("ref") else "port"
+    lo, ro, to = run(OracleBackend(configure(oracle.OracleGICP(variant, num_threads=threads))))
+    pairs = [(a, b) for a, b in zip(rg, ro) if a is not None and b is not None]
+    steady = tg[3:]
+    return {"scans": n, "points_per_scan": int(len(seq[0][0])), "path_m": float(np.linalg.norm(np.diff([s[1][0][:3, 3] for s in seq], axis=0), axis=1).sum()),
+            "ms_per_scan_median": 1e3 * float(np.median(steady)), "ms_per_scan_mean": 1e3 * float(np.mean(steady)), "scans_per_s": float(len(steady) / np.sum(steady)),
+            "keyframes": len(lg.keyframes), "max_submap_keyframes": max(len(r.submap) for r in rg if r is not None),
+            "submap_rebuilds": int(sum(1 for r in rg if r is not None and r.submap_changed)),
+            "lm_iterations_mean": float(np.mean([r.iterations + 1 for r in rg[1:] if r is not None])),
+            "max_abs_position_error_m": max(float(np.abs(r.T[:3, 3] - s[1][groups // 2][:3, 3]).max()) for r, s in zip(rg[1:], seq[1:]) if r is not None),
+            "oracle": {"kind": "port", "knn": "reference nanoflann.h" if variant == "ref" else "port k-d tree", "cores": threads,
+                       "ms_per_scan_median": 1e3 * float(np.median(to[3:])), "keyframes": len(lo.keyframes),
+                       "same_keyframe_decisions": int(sum(a.new_keyframe == b.new_keyframe for a, b in pairs)),
+                       "same_submap_sets": int(sum(a.submap == b.submap for a, b in pairs)),
+                       "same_iterations_and_convergence": int(sum(a.iterations == b.iterations and a.converged == b.converged for a, b in pairs)),
+                       "scans_compared": len(pairs),
+                       "max_pose_diff_m": max(float(np.abs(a.T[:3, 3] - b.T[:3, 3]).max()) for a, b in pairs),
+                       "max_rotation_entry_diff": max(float(np.abs(a.T[:3, :3] - b.T[:3, :3]).max()) for a, b in pairs)},
+            "note": "wall clock per callbackPointCloud incl. host policy (Python), H2D of the raw 32-byte records, D2H of the deskewed cloud"}
+
+
+def bulk_covariance_cfg3(g, scans, hbm, owned):
+    """BASELINE config 3: the covariances of a 16,777,216-point submap (256 keyframes x 65,536 points), keyframe i built by
+    rank i mod N — this rank's keyframes in ONE batched pass (every keyframe its own index, neighbours never cross keyframes:
+    the reference computes covariances per scan and concatenates them per submap, nano_gicp.cc:174-181, odom.cc:1719-1729)."""
+    from ngicp import synth
+    clouds = []
+    for i in owned:
+        rng = np.random.default_rng(9900 + i)          # keyframe i is the same cloud whatever the number of ranks
+        T = synth.se3((0, 0, rng.uniform(-np.pi, np.pi)), rng.uniform(-5, 5, 3) * [1, 1, 0.05])
+        clouds.append(synth.transform_points(T, scans[i % len(scans)]))
+    pts = np.concatenate(clouds)
+    del clouds
+    off = np.arange(len(owned) + 1, dtype=np.int64) * N_SCAN
+    g.enableTiming(True)
+    out = {}
+    for rep in range(3):
+        g.timings(reset=True)
+        t0 = time.perf_counter()
+        g.batchCovariances(pts, off)
+        wall = time.perf_counter() - t0
+        t = g.timings(reset=True)
+        out = {"points": int(len(pts)), "keyframes": len(owned), "index_ms": t["index_ms"], "knn_ms": t["knn_ms"], "covariance_ms": t["covariance_ms"],
+               "wall_ms_with_h2d_d2h": 1e3 * wall}
+    g.enableTiming(False)
+    n = len(pts)
+    dev_ms = out["index_ms"] + out["knn_ms"] + out["covariance_ms"]
+    out["covariance_mpts_s_device"] = n / (dev_ms * 1e-3) / 1e6
+    k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
+    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"],
+                          "traffic": ncu_traffic("bulk_K3"), "traffic_note": "ncu capture of a 64-keyframe (4,194,304-point) launch, scaled by points",
+                          "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
+    if out["roofline_K3"]["traffic"] is not None:
+        out["roofline_K3"]["traffic"] *= n / (64 * N_SCAN)
+    return out
 
 
 def bulk_covariance(g, scans, hbm, n_keyframes=64):

@@ -259,6 +259,9 @@ int ngicp_create(int device, ngicp_handle** out) {
   if (const char* e = std::getenv("NGICP_K2_LPQ")) h->k2_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_LPQ")) h->k4_lpq = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K2_LEAF")) h->k2_leaf = std::atoi(e);
+  if (const char* e = std::getenv("NGICP_K2_CAP2_MULT")) h->k2_cap2_mult = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("NGICP_FINE_OCC10")) h->fine_occ10 = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("NGICP_K2_TMA")) h->k2_tma = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K2_CHUNK")) h->k2_chunk = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_BALL")) h->k4_ball = std::atoi(e);
   if (const char* e = std::getenv("NGICP_K4_SPEC")) h->k4_spec = std::atoi(e);

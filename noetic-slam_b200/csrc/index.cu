@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(256) gather_levels_kernel(const float* __restr
 // cumulative entry count (this level and all coarser ones) fits the table. Fine level = as many finer levels below the
 // base level as still fit the table and still merge points (mean occupancy >= 1.11): a LiDAR scan is two orders of
 // magnitude denser next to the sensor than its mean, and there the self k-NN wants cells finer than the base level.
-__device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned int max_entries, int occupancy, bool want_fine, unsigned int* total_out, int* fine_out) {
+__device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned int max_entries, int occupancy, bool want_fine, int fine_occ10, unsigned int* total_out,
+                                           int* fine_out) {
   unsigned int cells[kNumLevels];
   unsigned int acc = 0;
   for (int L = kTopLevel; L >= 0; L--) {
@@ -221,7 +222,7 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
   }
   int fine = base;
   for (int L = base - 1; want_fine && L >= kSortLevel; L--) {
-    if ((unsigned long long)cells[L] * 10ull > (unsigned long long)n * 9ull) break;
+    if ((unsigned long long)cells[L] * (unsigned long long)fine_occ10 > (unsigned long long)n * 10ull) break;
     if (total + cells[L] > max_entries) break;
     total += cells[L];
     fine = L;
@@ -235,12 +236,12 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
 // the cell's slot by find-or-insert (atomicCAS on the key), so one pass over the sorted keys fills start AND end:
 // whichever of the two threads arrives first claims the slot, the fields they write are disjoint.
 __global__ void __launch_bounds__(256) table_build_kernel(const unsigned long long* __restrict__ keys, int n, GridMeta* __restrict__ meta,
-                                                          CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy, bool want_fine) {
+                                                          CellSlot* __restrict__ table, uint32_t mask, unsigned int max_entries, int occupancy, bool want_fine, int fine_occ10) {
   __shared__ int s_fine;
   if (threadIdx.x == 0) {
     unsigned int total;
     int fine;
-    const int b = choose_base(meta, n, max_entries, occupancy, want_fine, &total, &fine);
+    const int b = choose_base(meta, n, max_entries, occupancy, want_fine, fine_occ10, &total, &fine);
     s_fine = fine;
     if (blockIdx.x == 0) { meta->base_level = b; meta->fine_level = fine; meta->cells_total = total; }   // published for every later kernel
   }
@@ -371,7 +372,7 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
     keys_sorted = idx->keys;
   }
   gather_levels_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, keys_sorted, idx->pts, idx->inv, idx->meta);
-  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, fine ? cap / 2 + cap / 8 : cap / 2, 2, fine);
+  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, fine ? cap / 2 + cap / 8 : cap / 2, 2, fine, h->fine_occ10);
   count_launch(h, 2);
   IDX_CUDA(cudaGetLastError());
   IDX_CUDA(cudaEventCreateWithFlags(&idx->built, cudaEventDisableTiming));

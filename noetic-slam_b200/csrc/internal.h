@@ -100,10 +100,13 @@ struct ngicp_handle {
   size_t batch_partials_cap = 0;
   // tuning knobs (env NGICP_K4_CMAX / NGICP_K2_CMAX_MULT override)
   int k4_cmax = 64;
-  int k2_cmax_mult = 4;
+  int k2_cmax_mult = 6;
+  int fine_occ10 = 11;    // fine index levels are added while their mean occupancy stays >= fine_occ10 / 10 (NGICP_FINE_OCC10; 0: only the table limits)
+  int k2_tma = 1;         // candidate staging of the leaf search: TMA bulk copies (1) or direct loads (0) (NGICP_K2_TMA)
+  int k2_cap2_mult = 8;   // leaf rule of the leaf search: the parent of a leaf holds at most cap2 = k2_cap2_mult * cmax points (knn.cu)
   int k2_lpq = 0;   // lanes per query in K2 (0 = pick by cloud size)
   int k2_leaf = 1;  // leaf-scheduled K2 (lknn.cuh); NGICP_K2_LEAF=0 = the warp-cooperative search of round 1
-  int k2_chunk = 256;              // staging chunk of the leaf search (128 or 256)
+  int k2_chunk = 128;              // staging chunk of the leaf search (128 or 256)
   unsigned int* k2_ctr = nullptr;  // [4] item count / next item / finished warps of the leaf search (zero between calls)
   int k4_lpq = 0;
   int k4_ball = 1;  // seed re-association with the previous correspondences (NGICP_K4_BALL=0 disables)

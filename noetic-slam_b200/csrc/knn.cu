@@ -5,6 +5,9 @@
 // One thread per query; queries run in Morton order so that a warp walks the same few cells.
 // Distances are the reference's fp32 metric bit for bit (common.cuh: sqdist_ref); result rows are
 // ordered by (distance, original index).
+#include <cstdio>
+#include <cstdlib>
+
 #include "internal.h"
 #include "wknn.cuh"
 #include "lknn.cuh"
@@ -119,60 +122,136 @@ __global__ void __launch_bounds__(32 * kSelfWarps) knn_self_warp_kernel(GridView
 // ---- leaf-scheduled K2 (lknn.cuh) ---------------------------------------------------------------------------------
 // Work items of the search: one thread per sorted position; the heads of the finest grouping cells (level base+1) climb
 // to their leaf = the largest ancestor with <= cmax points (the finest grouping cell itself if even that holds more) and
-// the first point of a leaf appends ceil(members / 32) items. ctr[0] = number of items.
-__global__ void __launch_bounds__(256) leaf_items_kernel(GridView g, const unsigned long long* __restrict__ keys, int cmax,
+// the first point of a leaf appends ceil(members / 32) items. ctr[0] = number of items (see knn_leaf_kernel for the other counters).
+__global__ void __launch_bounds__(256) leaf_items_kernel(GridView g, const unsigned long long* __restrict__ keys, int cmax, int cap2,
                                                          LeafItem* __restrict__ items, unsigned int* __restrict__ ctr) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.n) return;
-  const int base = __ldg(&g.meta->fine_level);     // the finest level in the table
-  const unsigned long long key = __ldg(keys + j);
-  const int sh = 3 * (base + 1);
-  if (j > 0 && (__ldg(keys + j - 1) >> sh) == (key >> sh)) return;      // not the first point of its finest grouping cell
-  int P = min(base + 1, kTopLevel);
+  const int lane = threadIdx.x & 31;
+  int nit = 0, P = 0;
   uint32_t s = 0, e = 0;
-  if (!cell_lookup(g.table, g.table_mask, cell_key(key, P), s, e)) return;   // cannot happen: every cell >= base is in the table
-  while (P < kTopLevel) {
-    uint32_t s2, e2;
-    if (!cell_lookup(g.table, g.table_mask, cell_key(key, P + 1), s2, e2) || (int)(e2 - s2) > cmax) break;
-    P++; s = s2; e = e2;
+  if (j < g.n) {
+    const int base = __ldg(&g.meta->fine_level);     // the finest level in the table
+    const unsigned long long key = __ldg(keys + j);
+    const int sh = 3 * (base + 1);
+    if (j == 0 || (__ldg(keys + j - 1) >> sh) != (key >> sh)) {          // the first point of its finest grouping cell
+      // leaf = the largest ancestor P (from the finest grouping cell up) with <= cmax points whose parent holds <= cap2: the
+      // block staged for a leaf is about as populated as the leaf's parent and its neighbours, so a sparse cell inside a
+      // dense neighbourhood is taken at a finer level instead of dragging thousands of candidates through one warp. Both
+      // counts grow with the level, so every point of a leaf finds the same P.
+      P = min(base + 1, kTopLevel);
+      if (cell_lookup(g.table, g.table_mask, cell_key(key, P), s, e)) {   // (always: every cell >= base is in the table)
+        uint32_t s1 = 0, e1 = 0x7fffffffu;                                // the parent of the current candidate level
+        bool have1 = P < kTopLevel && cell_lookup(g.table, g.table_mask, cell_key(key, P + 1), s1, e1);
+        while (P < kTopLevel && have1 && (int)(e1 - s1) <= cmax) {
+          uint32_t s2 = 0, e2 = 0;
+          const bool have2 = P + 2 <= kTopLevel && cell_lookup(g.table, g.table_mask, cell_key(key, P + 2), s2, e2);
+          if (have2 && (int)(e2 - s2) > cap2) break;
+          P++; s = s1; e = e1;
+          s1 = s2; e1 = e2; have1 = have2;
+        }
+        if ((int)s == j) nit = ((int)(e - s) + 31) / 32;                  // the leaf belongs to its first point
+      }
+    }
   }
-  if ((int)s != j) return;                                                // the leaf belongs to its first point
-  const int mcount = (int)(e - s), nit = (mcount + 31) / 32;
-  const unsigned int at = atomicAdd(&ctr[0], (unsigned int)nit);
-  for (int c = 0; c < nit; c++) {
-    LeafItem it;
-    it.start = (int)s + 32 * c;
-    it.count_level = (min(32, mcount - 32 * c) << 8) | P;
-    it.pre = max((int)s, min(it.start, (int)e - 32));
-    it.pre_count = min(32, (int)e - it.pre);
-    items[at + c] = it;
+  // one atomic per warp: exclusive prefix of the item counts of its lanes
+  int inc = nit;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += a;
+  }
+  const int total = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned int at = 0;
+  if (total > 0) {
+    if (lane == 31) at = atomicAdd(&ctr[0], (unsigned int)total);
+    at = __shfl_sync(0xffffffffu, at, 31) + (unsigned int)(inc - nit);
+    const int mcount = (int)(e - s);
+    for (int c = 0; c < nit; c++) {
+      LeafItem it;
+      it.start = (int)s + 32 * c;
+      it.count_level = (min(32, mcount - 32 * c) << 8) | P;
+      items[at + c] = it;
+    }
+  }
+  // the last block to finish copies the item count to where the search keeps its queue state (knn_leaf_kernel)
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(&ctr[7], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    const unsigned int n1 = *reinterpret_cast<volatile unsigned int*>(&ctr[0]);
+    ctr[1] = n1; ctr[4] = n1; ctr[6] = n1; ctr[7] = 0u;
   }
 }
 
 constexpr int kLeafWarps = 4;
-// Persistent warps: every warp draws items from ctr[1] until the list is exhausted; the last warp to leave resets the
-// three counters, so the next k-NN call on this handle finds them zero without a memset.
+#ifndef NGICP_K2_MINB
+#define NGICP_K2_MINB 5      // CTAs per SM the leaf search is compiled for (register cap 96: at 80 the compiler rebuilds addresses from special registers inside the scan loop)
+#endif
+// Persistent warps over a work queue that the search itself may extend (leaf_knn_item re-queues the members of very
+// heavy blocks as smaller items). ctr: [0] items published and [1] next index of the overflow items (those published during
+// this launch, behind the n1 initial ones) — one 64-bit word, read with one load; [2] next ticket of the initial items,
+// [3] warps that left, [4] slots reserved, [6] n1, [7] block counter of leaf_items_kernel. Overflow items come first (they
+// are the pieces of the heaviest blocks: started late they would be the tail of the launch) and are drawn with a
+// compare-and-swap, so that an index is only ever consumed when its item exists; initial items with a plain atomicAdd.
+// Nobody waits: a warp leaves when both queues are empty at the moment it looks, and a warp that publishes items looks
+// again afterwards, so whatever nobody else picked up it processes itself. The last warp to leave resets the counters, so
+// the next k-NN call on this handle finds them zero without a memset.
 template <int KP, int KC, int C>
-__global__ void __launch_bounds__(32 * kLeafWarps) knn_leaf_kernel(GridView g, int k_rt, const LeafItem* __restrict__ items, unsigned int* __restrict__ ctr,
-                                                                   int normalization, bool tiled, int* __restrict__ nbr, double* __restrict__ dens_term) {
+__global__ void __launch_bounds__(32 * kLeafWarps, NGICP_K2_MINB) knn_leaf_kernel(GridView g, int k_rt, LeafItem* __restrict__ items, unsigned int capacity, unsigned int* __restrict__ ctr,
+                                                                   int normalization, bool tiled, int* __restrict__ nbr, double* __restrict__ dens_term,
+                                                                   unsigned long long* __restrict__ trace, int use_tma) {
+  unsigned long long t_enter = 0, t_first = 0, t_last = 0;
+  if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
   extern __shared__ __align__(16) unsigned char leaf_smem[];     // kLeafWarps x LeafScratch (dynamic: the big lists exceed 48 KB)
   LeafScratch<KP, C>& ws = reinterpret_cast<LeafScratch<KP, C>*>(leaf_smem)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int k = KC > 0 ? KC : k_rt;
-  if (lane == 0) { mbar_init(&ws.mbar[0], 1); mbar_init(&ws.mbar[1], 1); }
+  if (lane == 0) { mbar_init(&ws.mbar[0], 1); mbar_init(&ws.mbar[1], 1); ws.use_tma = use_tma; }
 #pragma unroll
-  for (int i = 0; i < kLeafPend; i++) ws.pend[i][lane] = __int_as_float(0x7f800000);
+  for (int i = 0; i < kLeafPend; i++) ws.pend[i][lane] = kKeyEmpty;
   __syncwarp();
   uint32_t phase = 0u;
-  const unsigned int n_items = *reinterpret_cast<volatile unsigned int*>(&ctr[0]);
+  volatile unsigned int* vctr = ctr;
+  const unsigned int n1 = vctr[6];
+  bool initial = true;
   for (;;) {
     unsigned int it = 0;
-    if (lane == 0) it = atomicAdd(&ctr[1], 1u);
+    bool got = false;
+    if (lane == 0) {
+      for (;;) {
+        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(ctr);
+        const unsigned int published = (unsigned int)w, t2 = (unsigned int)(w >> 32);
+        if (t2 < published) {                                       // an overflow item nobody has taken
+          if (atomicCAS(&ctr[1], t2, t2 + 1u) == t2) { it = t2; got = true; break; }
+          continue;
+        }
+        if (initial) { it = atomicAdd(&ctr[2], 1u); got = it < n1; initial = got; }
+        if (got || !initial) break;
+      }
+    }
+    got = __shfl_sync(0xffffffffu, got ? 1 : 0, 0) != 0;
     it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= n_items) break;
-    const LeafItem item = items[it];
+    if (!got) break;
+    if (trace && t_first == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+    LeafItem item;     // published by another SM during this launch, possibly: read through L2
+    {
+      const int2 raw = __ldcg(reinterpret_cast<const int2*>(items + it));
+      item.start = raw.x; item.count_level = raw.y;
+    }
+#ifdef NGICP_STATS
+    unsigned long long t_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    unsigned int* cur = g_leaf_cur[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & 8191];
+    if (lane == 0) { for (int i = 0; i < 8; i++) cur[i] = 0; }
+    __syncwarp();
+#endif
     leaf_knn_item<KP, KC, C>(g, item, k_rt, ws, phase, [&](int j, int (&a)[KP < 16 ? 16 : KP], double dsum) {
       sort_ascending(a);
+#pragma unroll
+      for (int i = 0; i < KP; i++) if (i < k - 1 && a[i] == 0x7fffffff) a[i] = j;   // fewer than k points in reach: pad with the point itself
       if (KC > 0 && (KC % 4) == 0 && tiled) {
 #pragma unroll
         for (int c = 0; c < KC / 4; c++) {
@@ -186,12 +265,56 @@ __global__ void __launch_bounds__(32 * kLeafWarps) knn_leaf_kernel(GridView g, i
         for (int i = 0; i + 1 < KP; i++) if (i + 1 < k) row[i + 1] = a[i];
       }
       if (dens_term) dens_term[j] = dsum / (double)normalization;
+    }, [&](unsigned heads, int level) {
+      // one new item per run of lanes; slots are reserved with one atomic, filled, and published in reservation order
+      const unsigned FULL = 0xffffffffu;
+      const int groups = __popc(heads);
+      unsigned int at = 0;
+      if (lane == 0) at = atomicAdd(&ctr[4], (unsigned int)groups);
+      at = __shfl_sync(FULL, at, 0);
+      if (at + (unsigned int)groups > capacity) {                 // no room: give the slots back in order and process the item as it is
+        if (lane == 0) { while (vctr[0] != at) __nanosleep(100); atomicSub(&ctr[4], (unsigned int)groups); }
+        __syncwarp();
+        return false;
+      }
+      if ((heads >> lane) & 1u) {
+        const unsigned above = heads & ~((2u << lane) - 1u);
+        const int end = above ? __ffs(above) - 1 : (item.count_level >> 8);
+        LeafItem ni;
+        ni.start = item.start + lane;
+        ni.count_level = ((end - lane) << 8) | level;
+        items[at + __popc(heads & ((1u << lane) - 1u))] = ni;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        while (vctr[0] != at) __nanosleep(100);                   // publish in reservation order
+        atomicAdd(&ctr[0], (unsigned int)groups);
+      }
+      __syncwarp();
+      return true;
     });
+#ifdef NGICP_STATS
+    if (lane == 0 && it < 8192) {
+      unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      g_leaf_items[4 * it] = t_start; g_leaf_items[4 * it + 1] = t_end;
+      g_leaf_items[4 * it + 2] = ((unsigned long long)(item.count_level & 0xff) << 56) | ((unsigned long long)(item.count_level >> 8) << 48) |
+                                 ((unsigned long long)min(cur[0], 255u) << 40) | ((unsigned long long)min(cur[3], 255u) << 32) | (unsigned long long)cur[1];
+      g_leaf_items[4 * it + 3] = ((unsigned long long)cur[2] << 32) | (unsigned long long)(unsigned)item.start;
+      if (it < 4096) { g_leaf_phase[4 * it] = cur[4]; g_leaf_phase[4 * it + 1] = cur[5]; g_leaf_phase[4 * it + 2] = cur[6]; g_leaf_phase[4 * it + 3] = cur[7]; }
+    }
+#endif
+    __syncwarp();
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+  }
+  if (trace && lane == 0) {     // development: [0] first warp entry, [1] last warp exit, [2] first item start, [3] last item end
+    unsigned long long t_exit; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+    atomicMin(&trace[0], t_enter); atomicMax(&trace[1], t_exit);
+    if (t_first) { atomicMin(&trace[2], t_first); atomicMax(&trace[3], t_last); }
   }
   if (lane == 0) {
-    __threadfence();
     const unsigned int total = gridDim.x * kLeafWarps;
-    if (atomicAdd(&ctr[2], 1u) == total - 1u) { ctr[0] = 0u; ctr[1] = 0u; __threadfence(); ctr[2] = 0u; }
+    if (atomicAdd(&ctr[3], 1u) == total - 1u) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = 0u; ctr[4] = 0u; ctr[6] = 0u; __threadfence(); ctr[3] = 0u; }
   }
 }
 
@@ -277,7 +400,8 @@ inline int group_cap_for(int k, int mult) { return k * mult > 32 ? k * mult : 32
 
 // persistent grid of the leaf search: as many CTAs as the device holds at once (queried once per instantiation)
 template <int KP, int KC, int C>
-static int launch_leaf_search(Handle* h, const Index* idx, int k, int normalization, const LeafItem* items, int* d_nbr, double* d_dens_term) {
+static int launch_leaf_search(Handle* h, const Index* idx, int k, int normalization, LeafItem* items, unsigned int capacity, int* d_nbr, double* d_dens_term,
+                              unsigned long long* d_trace) {
   static int per_sm = 0;
   constexpr size_t smem = sizeof(LeafScratch<KP, C>) * kLeafWarps;
   if (per_sm == 0) {
@@ -290,7 +414,7 @@ static int launch_leaf_search(Handle* h, const Index* idx, int k, int normalizat
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const int want = (idx->n / 16) / kLeafWarps + 1;     // an item is ~23 points on average
   const int grid = std::max(1, std::min(sms * per_sm, want));
-  knn_leaf_kernel<KP, KC, C><<<grid, 32 * kLeafWarps, smem, h->stream>>>(idx->view(), k, items, h->k2_ctr, normalization, nbr_tiled(k), d_nbr, d_dens_term);
+  knn_leaf_kernel<KP, KC, C><<<grid, 32 * kLeafWarps, smem, h->stream>>>(idx->view(), k, items, capacity, h->k2_ctr, normalization, nbr_tiled(k), d_nbr, d_dens_term, d_trace, h->k2_tma);
   return NGICP_OK;
 }
 
@@ -304,21 +428,46 @@ int knn_self(Handle* h, const Index* idx, int k, int* d_nbr, double* d_dens_term
   if (k <= 32 && h->k2_leaf) {
     // leaf-scheduled search (lknn.cuh): work items first, then the persistent search over them
     if (!h->k2_ctr) {
-      NGICP_CUDA(h, cudaMalloc(&h->k2_ctr, sizeof(unsigned int) * 4));
-      NGICP_CUDA(h, cudaMemsetAsync(h->k2_ctr, 0, sizeof(unsigned int) * 4, s));
+      NGICP_CUDA(h, cudaMalloc(&h->k2_ctr, sizeof(unsigned int) * 8));
+      NGICP_CUDA(h, cudaMemsetAsync(h->k2_ctr, 0, sizeof(unsigned int) * 8, s));
     }
     LeafItem* items = nullptr;
-    NGICP_CUDA(h, dev_alloc(&items, (size_t)n + (size_t)n / 32 + 1, s));
-    leaf_items_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, idx->keys, group_cap_for(k, h->k2_cmax_mult), items, h->k2_ctr);
+    const size_t capacity = (size_t)n + (size_t)n / 32 + (size_t)n / 4 + 64;     // leaves + their 32-point chunks + room for re-queued splits
+    NGICP_CUDA(h, dev_alloc(&items, capacity, s));
+    static const bool trace = std::getenv("NGICP_K2_TRACE") != nullptr;      // development: split of the two launches
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
+    leaf_items_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, idx->keys, group_cap_for(k, h->k2_cmax_mult), group_cap_for(k, h->k2_cmax_mult) * h->k2_cap2_mult, items,
+                                                    h->k2_ctr);
+    unsigned long long* d_trace = nullptr;
+    if (trace) {
+      cudaEventRecord(ev[1], s);
+      cudaMalloc(&d_trace, 32);
+      const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+      cudaMemcpyAsync(d_trace, init, 32, cudaMemcpyHostToDevice, s);
+      cudaEventRecord(ev[1], s);
+    }
     int rc;
-#define LEAF(KP, KC) (h->k2_chunk == 128 ? launch_leaf_search<KP, KC, 128>(h, idx, k, normalization, items, d_nbr, d_dens_term) \
-                                         : launch_leaf_search<KP, KC, 256>(h, idx, k, normalization, items, d_nbr, d_dens_term))
+#define LEAF(KP, KC) (h->k2_chunk == 128 ? launch_leaf_search<KP, KC, 128>(h, idx, k, normalization, items, (unsigned int)capacity, d_nbr, d_dens_term, d_trace) \
+                                         : launch_leaf_search<KP, KC, 256>(h, idx, k, normalization, items, (unsigned int)capacity, d_nbr, d_dens_term, d_trace))
     if (k == 16) rc = LEAF(16, 16);
     else if (k == 20) rc = LEAF(32, 20);
     else if (k <= 8) rc = LEAF(8, 0);
     else if (k <= 16) rc = LEAF(16, 0);
     else rc = LEAF(32, 0);
 #undef LEAF
+    if (trace) {
+      cudaEventRecord(ev[2], s);
+      cudaEventSynchronize(ev[2]);
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+      unsigned long long t[4];
+      cudaMemcpy(t, d_trace, sizeof t, cudaMemcpyDeviceToHost);
+      cudaFree(d_trace);
+      std::fprintf(stderr, "[k2 trace] n %d leaf_items %.3f ms search %.3f ms (events); in-kernel: enter..exit %.1f us, first item at +%.1f us, last item end at +%.1f us\n", n, a, b,
+                   (t[1] - t[0]) * 1e-3, (t[2] - t[0]) * 1e-3, (t[3] - t[0]) * 1e-3);
+      for (auto& e : ev) cudaEventDestroy(e);
+    }
     dev_free(items, s);
     if (rc) return rc;
     count_launch(h, 2);
@@ -374,6 +523,29 @@ int knn_queries(Handle* h, const Index* idx, const float4* d_q, int nq, int k, i
 }  // namespace ngicp
 
 #ifdef NGICP_STATS
+extern "C" int ngicp_debug_stats_leaf(unsigned long long out[16], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_leaf_stats, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ngicp::g_leaf_stats, z, sizeof z); }
+  return 0;
+}
+extern "C" int ngicp_debug_leaf_phase(unsigned int* out, int n_items) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_leaf_phase, sizeof(unsigned int) * 4 * n_items);
+  return 0;
+}
+extern "C" int ngicp_debug_leaf_items(unsigned long long* out, int n_items) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_leaf_items, sizeof(unsigned long long) * 4 * n_items);
+  return 0;
+}
+extern "C" int ngicp_debug_leaf_records(unsigned int* out /* 64 x 24 */, unsigned int* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ngicp::g_leaf_dbg, sizeof(unsigned int) * 64 * 24);
+  cudaMemcpyFromSymbol(n, ngicp::g_leaf_dbg_n, sizeof(unsigned int));
+  unsigned int z = 0; cudaMemcpyToSymbol(ngicp::g_leaf_dbg_n, &z, sizeof z);
+  return 0;
+}
 extern "C" int ngicp_debug_items_knn(unsigned long long* out, int n_items) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, ngicp::g_k2_items, sizeof(unsigned long long) * 4 * n_items);

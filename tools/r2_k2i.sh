@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_k2.py -q 2>&1 | tail -5 > gpurun_out/k2_tests.txt; cat gpurun_out/k2_tests.txt
+NGICP_K2_TRACE=1 timeout 300 python tools/ab.py k3 2>&1 | grep -E "^K3|k2 trace" | tail -3 > gpurun_out/trace.txt
+NGICP_K2_TRACE=1 timeout 300 python tools/gpu_diag.py --big 2>&1 | grep -E "^run 2|k2 trace" | tail -3 >> gpurun_out/trace.txt
+cat gpurun_out/trace.txt
+for w in diag degenerate; do
+NGICP_LIB=$PWD/noetic-slam_b200/libngicp_b200_stats.so timeout 300 python tools/leaf_items.py $w 2>&1 | grep -v "^\[" | head -24
+done > gpurun_out/leaf_items.txt; cat gpurun_out/leaf_items.txt
