@@ -21,6 +21,8 @@ constexpr int kNumLevels = kTopLevel + 1;         // levels 0..12
 constexpr int kMaxSegBits = 20;                   // keyframes per batched index
 constexpr int kSortLevel = 0;                     // keys are sorted on all 36 bits (four 9-bit passes): where a scan is dense (the
                                                   // returns next to the sensor) the self k-NN needs cells finer than the base level
+constexpr int kBaseFloor = 3;                     // the base level (correspondence / public searches) is never finer than this:
+                                                  // 512 cells per axis; the bounded 1-NN search is tuned to cells of that size
 constexpr int kMaxCoord = (1 << kBitsPerAxis) - 1;
 constexpr unsigned long long kEmptyKey = ~0ull;
 

@@ -214,7 +214,7 @@ __device__ __forceinline__ int choose_base(const GridMeta* meta, int n, unsigned
   }
   int base = kTopLevel;
   unsigned int total = cells[kTopLevel];
-  for (int L = kTopLevel - 1; L >= kSortLevel; L--) {
+  for (int L = kTopLevel - 1; L >= kBaseFloor; L--) {
     if ((unsigned long long)cells[L] * (unsigned)occupancy > (unsigned long long)n) break;
     if (total + cells[L] > max_entries) break;
     total += cells[L];

@@ -8,3 +8,11 @@ print("bulk: index", round(b["index_ms"], 3), "knn", round(b["knn_ms"], 3), "cov
       "batch corr", round(b["batch_correspond_ms"], 3), "batch lin", round(b["batch_linearize_ms"], 4), "K4b frac", round(b["roofline_K4b"]["frac"], 3))
 print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in b.items() if k.startswith("prefilter")})
 print(b.get("multi_sequence"))
+
+print("e2e_pageable", d.get("e2e_pageable"))
+print("e2e_cpp_dropin", d.get("e2e_cpp_dropin"))
+print("bulk.all_ranks", b.get("all_ranks"))
+print("multi_sequence_8", d.get("multi_sequence_8"))
+print("odom_loop_cfg4", d.get("odom_loop_cfg4"))
+print("cpu", d.get("cpu_baseline"))
+print("per_rank", d.get("per_rank_step_ms_median_min_max"), "clocks", d.get("clocks"))
