@@ -158,13 +158,19 @@ class NanoGICP : public LsqRegistration<PointSource, PointTarget> {
     // reference's (fp32, ((m0 x + m1 y) + m2 z) + m3 per row); DLIO discards the result (odom.cc:1004-1005) and may switch
     // it off with setComputeOutputCloud(false).
     if (compute_output_) {
-      output = *input_;
+      // pcl::Registration::align has already copied *input_ into `output` (every field); only xyz is rewritten, from input_
+      if (output.points.size() != input_->points.size()) output = *input_;
       const Matrix4& M = final_transformation_;
-      for (auto& pt : output.points) {
-        const float x = pt.x, y = pt.y, z = pt.z;
-        pt.x = ((M(0, 0) * x + M(0, 1) * y) + M(0, 2) * z) + M(0, 3);
-        pt.y = ((M(1, 0) * x + M(1, 1) * y) + M(1, 2) * z) + M(1, 3);
-        pt.z = ((M(2, 0) * x + M(2, 1) * y) + M(2, 2) * z) + M(2, 3);
+      const float m00 = M(0, 0), m01 = M(0, 1), m02 = M(0, 2), m03 = M(0, 3), m10 = M(1, 0), m11 = M(1, 1), m12 = M(1, 2), m13 = M(1, 3);
+      const float m20 = M(2, 0), m21 = M(2, 1), m22 = M(2, 2), m23 = M(2, 3);
+      const size_t n = input_->points.size();
+      const PointSource* in = input_->points.data();
+      PointSource* out = output.points.data();
+      for (size_t i = 0; i < n; i++) {
+        const float x = in[i].x, y = in[i].y, z = in[i].z;
+        out[i].x = ((m00 * x + m01 * y) + m02 * z) + m03;
+        out[i].y = ((m10 * x + m11 * y) + m12 * z) + m13;
+        out[i].z = ((m20 * x + m21 * y) + m22 * z) + m23;
       }
     }
   }

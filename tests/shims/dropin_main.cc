@@ -63,5 +63,29 @@ int main(int argc, char** argv) {
   std::printf("filtered %zu first %.9g %.9g %.9g T", filtered->points.size(), filtered->points[0].x, filtered->points[0].y, filtered->points[0].z);
   for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) std::printf(" %.9g", T2(r, c));
   std::printf("\n");
+  // the hand-over DLIO actually makes (odom.cc:1737-1738 -> :992-998): the submap tree is built on gicp_temp and adopted by
+  // gicp WITHOUT anything on gicp_temp that waits for the build (no calculateTargetCovariances there: the submap's
+  // covariances are the keyframes'); the adopter must order itself after the build
+  {
+    nano_gicp::NanoGICP<Point, Point> a, b;
+    for (auto* g : {&a, &b}) {
+      g->setCorrespondenceRandomness(16);
+      g->setMaxCorrespondenceDistance(0.5);
+      g->setMaximumIterations(32);
+      g->setTransformationEpsilon(0.01);
+      g->setRotationEpsilon(0.01);
+    }
+    b.setInputTarget(tgt);                       // index build in flight on b's stream
+    a.registerInputTarget(tgt);
+    a.target_kdtree_ = b.target_kdtree_;         // adopted at once
+    a.setTargetCovariances(submap_normals);
+    a.setInputSource(src);
+    a.calculateSourceCovariances();
+    a.align(aligned);
+    const auto T3 = a.getFinalTransformation();
+    std::printf("handover T");
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) std::printf(" %.9g", T3(r, c));
+    std::printf("\n");
+  }
   return 0;
 }

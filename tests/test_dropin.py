@@ -14,18 +14,22 @@ ROOT = Path(__file__).resolve().parent.parent
 CXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
 
 
-def build_dropin(tmp_path):
-    exe = tmp_path / "dropin_main"
+def build_dropin(tmp_path, pcl_minor=10, source="dropin_main.cc"):
+    """pcl_minor 10: the PCL <= 1.10 flavour of the shims (cloud pointers are a distinct boost::shared_ptr template, as in
+    DLIO's Ubuntu 20.04 image); 12: PCL >= 1.11 (std::shared_ptr). A std/boost mix-up in the headers fails to compile."""
+    exe = tmp_path / f"{Path(source).stem}_{pcl_minor}"
     lib = ROOT / "noetic-slam_b200" / "libngicp_b200.so"
-    cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{ROOT / 'tests' / 'shims'}", f"-I{ROOT / 'include'}",
-           str(ROOT / "tests" / "shims" / "dropin_main.cc"), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-Werror", f"-DSHIM_PCL_MINOR={pcl_minor}", f"-I{ROOT / 'tests' / 'shims'}", f"-I{ROOT / 'include'}",
+           str(ROOT / "tests" / "shims" / source), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
 
 
-def test_dropin_headers_compile_and_link(tmp_path):
-    assert build_dropin(tmp_path).exists()
+@pytest.mark.parametrize("pcl_minor", [10, 12])
+def test_dropin_headers_compile_and_link(tmp_path, pcl_minor):
+    assert build_dropin(tmp_path, pcl_minor).exists()
+    assert build_dropin(tmp_path, pcl_minor, "dropin_bench.cc").exists()
 
 
 @pytest.mark.gpu
@@ -60,3 +64,8 @@ def test_dropin_matches_python_mirror(tmp_path):
     assert int(f[1]) == len(filt) and (np.array([float(x) for x in f[3:6]], np.float32) == filt[0]).all()
     T2_cpp = np.array([float(x) for x in f[7:23]]).reshape(4, 4)
     assert np.abs(T2_cpp - T2).max() < 1e-6
+    # the tree handed from one NanoGICP object to another right after its build was launched (stream ordering)
+    hv = lines[3].split()
+    assert hv[0] == "handover"
+    T3_cpp = np.array([float(x) for x in hv[2:18]]).reshape(4, 4)
+    assert np.abs(T3_cpp - T).max() < 1e-6
