@@ -504,8 +504,11 @@ def drive_loop(loop, seq, drift, groups, i0, i1, ts=None, res=None):
         rec, Ts, block, col_t = seq[i]
         t0 = time.perf_counter()
         if i == 0:
-            loop.T = Ts[groups // 2].astype(np.float32)
-            loop.propagateGICP()
+            if hasattr(loop, "set_pose"):
+                loop.set_pose(Ts[groups // 2])
+            else:
+                loop.T = Ts[groups // 2].astype(np.float32)
+                loop.propagateGICP()
             r = loop.callbackPointCloud(rec, None)
         else:
             def prior(stamps, Ts=Ts, i=i):
@@ -529,7 +532,7 @@ def multi_sequence_cfg5(device, rank, world, seqs, owned, barrier, reduce_job):
     loops, drifts = [], []
     for k, seq in zip(owned, seqs):
         g = configure(ngicp.NanoGICP(device))
-        loops.append(odom.OdomLoop(odom.DeviceBackend(g), odom.OdomParams()))
+        loops.append(odom.NativeOdomLoop(g, odom.OdomParams()))
         rng = np.random.default_rng(1000 + k)
         drifts.append([synth.random_se3(rng, 0.03, 0.3) for _ in range(len(seq))])
     results = [[] for _ in loops]
@@ -540,7 +543,7 @@ def multi_sequence_cfg5(device, rank, world, seqs, owned, barrier, reduce_job):
     def worker(loop, seq, dr, res):
         gate.wait()
         drive_loop(loop, seq, dr, 1, warm, len(seq), res=res)
-        loop.b.gicp.synchronize()
+        loop.gicp.synchronize()
 
     ths = [threading.Thread(target=worker, args=a) for a in zip(loops, seqs, drifts, results)]
     for t in ths:
@@ -558,10 +561,10 @@ def multi_sequence_cfg5(device, rank, world, seqs, owned, barrier, reduce_job):
     e_max, _ = reduce_job(err, 0.0)
     return {"sequences": CFG5_SEQUENCES, "scans_per_sequence": len(seqs[0]) if seqs else 0, "timed_scans_all_ranks": int(u_all), "ranks": world,
             "sequences_on_this_rank": len(seqs), "scans_per_s": u_all / t_max, "wall_s_max_over_ranks": t_max, "scaling": "strong (8 sequences in total)",
-            "keyframes_rank0": [len(l.keyframes) for l in loops], "lm_iterations_mean_rank0": float(np.mean(its)) if its else None,
+            "keyframes_rank0": [l.n_keyframes for l in loops], "lm_iterations_mean_rank0": float(np.mean(its)) if its else None,
             "max_abs_position_error_m": e_max,
             "note": "MulRan-shaped 65,536-point records (t = 0), full per-scan loop (ingest, deskew, VoxelGrid, index, covariances, align, keyframes, "
-                    "submap rebuilds); host policy is Python, H2D of the raw records and D2H of the deskewed cloud included"}
+                    "submap rebuilds); host policy in C++ (ngicp_odom_*, csrc/odom_loop.cu), the prior poses come from a Python callback; H2D of the raw records included"}
 
 
 def odom_loop_cfg4(device, seq, groups=2):
@@ -578,12 +581,20 @@ def odom_loop_cfg4(device, seq, groups=2):
     drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
 
     def run(backend):
-        loop = odom.OdomLoop(backend, odom.OdomParams())
+        loop = odom.OdomLoop(backend, odom.OdomParams()) if backend is not None else odom.NativeOdomLoop(configure(ngicp.NanoGICP(device)), odom.OdomParams())
         ts, res = [], []
         drive_loop(loop, seq, drift, groups, 0, n, ts, res)
         return loop, res, ts
 
     lg, rg, tg = run(odom.DeviceBackend(configure(ngicp.NanoGICP(device))))
+    ln, rn, tn = run(None)
+    both = [(a, b) for a, b in zip(rn, rg) if a is not None and b is not None]
+    cpp = {"ms_per_scan_median": 1e3 * float(np.median(tn[3:])), "ms_per_scan_mean": 1e3 * float(np.mean(tn[3:])), "scans_per_s": float(len(tn[3:]) / np.sum(tn[3:])),
+           "keyframes": ln.n_keyframes, "stage_ms_mean": ln.profile(), "scans_compared_with_python_loop": len(both),
+           "same_decisions_as_python_loop": int(sum(a.new_keyframe == b.new_keyframe and a.submap == b.submap and a.iterations == b.iterations
+                                                    and a.converged == b.converged and a.n_points == b.n_points for a, b in both)),
+           "max_pose_diff_m": max(float(np.abs(a.T[:3, 3] - b.T[:3, 3]).max()) for a, b in both),
+           "note": "the same loop in C++ behind the C ABI (ngicp_odom_scan_begin / _finish); the prior poses still come from a Python callback"}
     threads = os.cpu_count() or 1
     variant = "ref" if oracle.available("ref") else "port"
     lo, ro, to = run(OracleBackend(configure(oracle.OracleGICP(variant, num_threads=threads))))
@@ -595,6 +606,7 @@ def odom_loop_cfg4(device, seq, groups=2):
             "submap_rebuilds": int(sum(1 for r in rg if r is not None and r.submap_changed)),
             "lm_iterations_mean": float(np.mean([r.iterations + 1 for r in rg[1:] if r is not None])),
             "max_abs_position_error_m": max(float(np.abs(r.T[:3, 3] - s[1][groups // 2][:3, 3]).max()) for r, s in zip(rg[1:], seq[1:]) if r is not None),
+            "cpp_loop": cpp,
             "oracle": {"kind": "port", "knn": "reference nanoflann.h" if variant == "ref" else "port k-d tree", "cores": threads,
                        "ms_per_scan_median": 1e3 * float(np.median(to[3:])), "keyframes": len(lo.keyframes),
                        "same_keyframe_decisions": int(sum(a.new_keyframe == b.new_keyframe for a, b in pairs)),
@@ -691,8 +703,11 @@ def odom_loop_probe(device, n_scans=24):
     for i, (rec, Ts, block, col_t) in enumerate(seq):
         t0 = time.perf_counter()
         if i == 0:
-            loop.T = Ts[groups // 2].astype(np.float32)
-            loop.propagateGICP()
+            if hasattr(loop, "set_pose"):
+                loop.set_pose(Ts[groups // 2])
+            else:
+                loop.T = Ts[groups // 2].astype(np.float32)
+                loop.propagateGICP()
             r = loop.callbackPointCloud(rec, None)
         else:
             def prior(stamps, Ts=Ts, i=i):

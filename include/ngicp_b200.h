@@ -220,6 +220,62 @@ int ngicp_scan_ingest(ngicp_handle* h, const void* points, size_t n, size_t stri
                       const float crop_min[3], const float crop_max[3], int crop_negative, double* unique_stamps, size_t* n_unique, size_t* n_kept);
 int ngicp_scan_deskew(ngicp_handle* h, const float* frames16, size_t n_frames, const float leaf[3], int set_as, float* out_xyz, size_t* n_out);
 
+/* ---- host loop of one odometry sequence (BASELINE configs 4 and 5) --------------------------------
+ * The GICP-relevant part of dlio::OdomNode's per-scan callback, in C++ over the calls above: callbackPointCloud
+ * (odom.cc:737-837), computeSpaciousness / computeDensity / setAdaptiveParams (:1398-1436, :1600-1626), getNextPose
+ * (:984-1018), propagateGICP (:1230-1246), updateKeyframes (:1517-1598), pushSubmapIndices / buildSubmap /
+ * buildKeyframesAndSubmap (:1628-1780), computeConvexHull / computeConcaveHull (:1438-1515). IMU integration and the
+ * geometric observer stay with the caller: one scan is TWO calls so that the caller can integrate its IMU buffer at the
+ * unique time stamps in between (odom.cc:671-672).
+ *   scan_begin   removeNaN + CropBox (negative, +-crop_size) + time sort on the device; returns the unique stamps
+ *                (capacity n doubles) and keeps the planar ranges of the cropped scan for computeSpaciousness
+ *   scan_finish  frames16 = n_unique column-major fp32 world poses of the sensor (or one, or NULL = "no IMU": the current
+ *                pose, odom.cc:656-664); deskew + VoxelGrid + setInputSource, metrics + adaptive parameters, source
+ *                covariances, align against the current submap, pose propagation, keyframe decision, keyframe capture /
+ *                transform and submap re-assembly, all without the scan or a covariance leaving HBM.
+ * res->valid == 0: the scan was dropped (empty after the crop, or <= gicp_min_num_points points, odom.cc:764-767).
+ * Planar keyframe sets (pcl::ConvexHull's 2-D case) are handled inside; for spatial sets the caller installs the two hull
+ * callbacks (indices of the points on the hull of n xyz doubles; return the count or < 0), else scan_finish fails with
+ * NGICP_ERR_UNSUPPORTED. One ngicp_odom owns its handle's source, target and keyframes for its lifetime. */
+typedef struct ngicp_odom ngicp_odom;
+typedef struct ngicp_odom_params {
+  float crop_size;             /* preprocessing/cropBoxFilter/size   (cfg/params.yaml:43) */
+  float voxel_res;             /* preprocessing/voxelFilter/res      (:45); <= 0: no voxel grid */
+  float keyframe_thresh_dist;  /* keyframe/threshD                   (:48) */
+  float keyframe_thresh_rot;   /* keyframe/threshR, degrees          (:49) */
+  int submap_knn, submap_kcv, submap_kcc; /* submap/keyframe/{knn,kcv,kcc} (:53-55) */
+  int gicp_min_num_points;     /* gicp/minNumPoints                  (:57) */
+  float gicp_max_corr_dist;    /* gicp/maxCorrespondenceDistance     (:59) */
+  int adaptive;                /* adaptive                           (cfg/dlio.yaml:17) */
+  int time_offset_bytes;       /* byte offset and type (as ngicp_scan_ingest) of the per-point time stamp */
+  int time_type;
+} ngicp_odom_params;
+typedef struct ngicp_odom_result {
+  int valid;
+  float T[16];        /* lidar pose after the scan, column-major */
+  float T_corr[16];   /* the alignment's correction, column-major */
+  int converged, iterations, n_points;
+  int new_keyframe, submap_changed; /* submap_changed: the submap this scan was aligned against differs from the previous scan's */
+  int n_keyframes, n_submap;
+} ngicp_odom_result;
+typedef int (*ngicp_hull_fn)(const double* xyz, int n, double alpha, int* out_indices, void* user);
+void ngicp_odom_default_params(ngicp_odom_params* p);
+int ngicp_odom_create(ngicp_handle* h, const ngicp_odom_params* p, ngicp_odom** out);
+int ngicp_odom_destroy(ngicp_odom* o);
+const char* ngicp_odom_last_error(const ngicp_odom* o);
+int ngicp_odom_set_hull_callbacks(ngicp_odom* o, ngicp_hull_fn convex, ngicp_hull_fn concave, void* user);
+int ngicp_odom_set_pose(ngicp_odom* o, const float T_colmajor[16]);
+int ngicp_odom_scan_begin(ngicp_odom* o, const void* records, size_t n, size_t stride_bytes, double* unique_stamps, size_t* n_unique, size_t* n_kept);
+/* host wall clock per stage of the loop, seconds summed over `scans` valid scans: 0 ingest (crop + time sort, waits for the
+ * stamps), 1 planar ranges, 2 deskew + VoxelGrid + index build (waits for the point count), 3 median + adaptive parameters,
+ * 4 source covariances (waits for the density), 5 align, 6 keyframe decision + capture, 7 keyframe transform + hulls + submap */
+#define NGICP_ODOM_STAGES 8
+int ngicp_odom_get_profile(ngicp_odom* o, double seconds[NGICP_ODOM_STAGES], long* scans, int reset);
+/* the planar hull used inside (exported for tests): indices (ascending) of the points on the convex hull (concave == 0)
+ * or on the alpha shape of n xyz doubles; returns the count, -3 when the set is spatial (callback case), -1 on bad input */
+int ngicp_hull_planar(const double* xyz, int n, int concave, double alpha, int* out_indices);
+int ngicp_odom_scan_finish(ngicp_odom* o, const float* frames16, size_t n_frames, ngicp_odom_result* res, int* submap_ids, int submap_cap);
+
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */
 typedef struct ngicp_timings {
   float index_ms;       /* K1: keys + radix sort + reorder + voxel hash   */

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kFiltThreads) crop_count_kernel(const float* _
 
 // exclusive scan of the block sums by one block; the grand total goes to the host-mapped slot
 __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restrict__ sums, int nblocks, unsigned int* __restrict__ total_dev,
-                                                         ReduceSlot* __restrict__ slot, unsigned long long seq) {
+                                                         ReduceSlot* __restrict__ slot, unsigned long long seq, const int* __restrict__ flag = nullptr) {
   __shared__ unsigned int s[1024];
   __shared__ unsigned int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
   if (threadIdx.x == 0) {
     *total_dev = carry;
     slot->v[0] = (double)carry;
+    slot->v[1] = flag ? (double)*flag : 0.0;     // rides along with the count (the voxel grid's overflow flag)
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&slot->seq) = seq;
   }
@@ -353,6 +354,11 @@ __global__ void __launch_bounds__(kFiltThreads) deskew_apply_kernel(const float4
 __global__ void zero_u32_kernel(unsigned int* p) { *p = 0u; }
 
 int wait_count(Handle* h, unsigned long long seq, size_t* out) {
+  if (h->overlap_fn) {                 // the kernels are in flight: the caller's host work goes here
+    auto fn = h->overlap_fn;
+    h->overlap_fn = nullptr;
+    fn(h->overlap_arg);
+  }
   volatile unsigned long long* p = &h->slot_host[0].seq;
   unsigned long long spins = 0;
   while (*p != seq) {
@@ -423,16 +429,12 @@ int voxel_grid_device(Handle* h, const float* d_in, int stride, int n, const flo
   NGICP_CUDA(h, dev_alloc(d_out, (size_t)n, s));
   const unsigned long long seq = ++h->seq;
   vg_count_kernel<<<nb, kFiltThreads, 0, s>>>(keys_sorted, n, d_sums);
-  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq, &meta->overflow);
   vg_centroid_kernel<<<nb, kFiltThreads, 0, s>>>(d_in, stride, n, keys_sorted, vals_sorted, d_sums, *d_out, d_out_voxel);
   count_launch(h, 3);
   NGICP_CUDA(h, cudaGetLastError());
   int rc = wait_count(h, seq, n_out);
-  int overflow = 0;
-  if (!rc) {
-    NGICP_CUDA(h, cudaMemcpyAsync(&overflow, &meta->overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
-    NGICP_CUDA(h, cudaStreamSynchronize(s));
-  }
+  const int overflow = !rc && h->slot_host[0].v[1] != 0.0;
   dev_free(d_sums, s);
   dev_free(scratch, s);
   if (!rc && overflow) {
@@ -519,7 +521,11 @@ int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stri
   Box box;
   for (int a = 0; a < 3; a++) { box.mn[a] = crop_min ? crop_min[a] : 0.f; box.mx[a] = crop_max ? crop_max[a] : 0.f; }
   box.negative = crop_negative;
-  const int nbits = time_type == 2 ? 64 : 33;   // bit 32 separates the dropped points (all-ones key) from real 32-bit stamps
+  // bit 32 separates the dropped points (all-ones key) from real 32-bit stamps; when the caller knows that every uint32 stamp
+  // is < 2^b, bit b does (fewer sort passes: an OS1 scan spans 1e8 ns = 27 bits, a MulRan scan has one stamp)
+  int nbits = time_type == 2 ? 64 : 33;
+  if (time_type == 0 && h->ingest_stamp_bits >= 0 && h->ingest_stamp_bits < 32) nbits = h->ingest_stamp_bits + 1;
+  h->ingest_stamp_bits = -1;
   const int passes = sort_num_passes(nbits);
   unsigned char* d_recs = nullptr;
   unsigned long long *keys_a = nullptr, *keys_b = nullptr;
@@ -590,15 +596,14 @@ int ngicp_scan_deskew(ngicp_handle* p, const float* frames16, size_t n_frames, c
   NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 2, s));
   NGICP_CUDA(h, dev_alloc(&d_out, (size_t)n, s));
   NGICP_CUDA(h, cudaMemcpyAsync(d_frames, frames16, sizeof(float) * 16 * n_frames, cudaMemcpyHostToDevice, s));
-  const unsigned long long seq = ++h->seq;
+  const unsigned long long seq = ++h->seq;     // the group count is known since the ingest: nobody waits for this one
   zero_u32_kernel<<<1, 1, 0, s>>>(d_sums + nb + 1);
   ingest_count_kernel<<<nb, kFiltThreads, 0, s>>>(h->scan_keys, n, d_sums, d_sums + nb + 1);
   scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, nb, d_sums + nb, h->slot_dev, seq);
   deskew_apply_kernel<<<nb, kFiltThreads, 0, s>>>(h->scan_pts, h->scan_keys, n, d_sums, d_frames, (int)n_frames, d_out);
   count_launch(h, 4);
   NGICP_CUDA(h, cudaGetLastError());
-  size_t groups = 0;
-  int rc = wait_count(h, seq, &groups);
+  int rc = NGICP_OK;
   const float* cur = reinterpret_cast<const float*>(d_out);
   size_t cur_n = (size_t)n;
   if (!rc && leaf) {

@@ -96,6 +96,10 @@ struct ngicp_handle {
   bool async_input = false;
   bool input_pending = false;
   cudaEvent_t input_copied = nullptr;
+  // host work the odom loop (odom_loop.cu) wants done while the device is busy: run once by the next wait_count (filters.cu)
+  void (*overlap_fn)(void*) = nullptr;
+  void* overlap_arg = nullptr;
+  int ingest_stamp_bits = -1;   // uint32 stamps of the next ngicp_scan_ingest are all < 2^bits (the caller looked); -1: unknown
   double* batch_partials = nullptr;  // batched reductions (allocated on first use)
   size_t batch_partials_cap = 0;
   // tuning knobs (env NGICP_K4_CMAX / NGICP_K2_CMAX_MULT override)

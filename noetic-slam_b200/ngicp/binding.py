@@ -28,6 +28,8 @@ SYMBOLS = [
     "ngicp_linearize", "ngicp_compute_error", "ngicp_align", "ngicp_transform_source", "ngicp_batch_covariances", "ngicp_set_input_batch", "ngicp_batch_linearize",
     "ngicp_keyframe_capture", "ngicp_keyframe_transform", "ngicp_keyframe_size", "ngicp_keyframe_release", "ngicp_keyframe_download",
     "ngicp_submap_assemble", "ngicp_filter_scan", "ngicp_scan_ingest", "ngicp_scan_deskew",
+    "ngicp_odom_default_params", "ngicp_odom_create", "ngicp_odom_destroy", "ngicp_odom_last_error", "ngicp_odom_set_hull_callbacks",
+    "ngicp_odom_set_pose", "ngicp_odom_get_profile", "ngicp_odom_scan_begin", "ngicp_odom_scan_finish", "ngicp_hull_planar",
     "ngicp_enable_timing", "ngicp_get_timings",
 ]
 
@@ -42,6 +44,20 @@ class Timings(C.Structure):
     _fields_ = [("index_ms", C.c_float), ("knn_ms", C.c_float), ("covariance_ms", C.c_float), ("linearize_ms", C.c_float),
                 ("error_ms", C.c_float), ("linearize_calls", C.c_int), ("error_calls", C.c_int), ("kernel_launches", C.c_int),
                 ("correspond_ms", C.c_float)]
+
+
+class OdomParamsC(C.Structure):
+    _fields_ = [("crop_size", C.c_float), ("voxel_res", C.c_float), ("keyframe_thresh_dist", C.c_float), ("keyframe_thresh_rot", C.c_float),
+                ("submap_knn", C.c_int), ("submap_kcv", C.c_int), ("submap_kcc", C.c_int), ("gicp_min_num_points", C.c_int),
+                ("gicp_max_corr_dist", C.c_float), ("adaptive", C.c_int), ("time_offset_bytes", C.c_int), ("time_type", C.c_int)]
+
+
+class OdomResultC(C.Structure):
+    _fields_ = [("valid", C.c_int), ("T", C.c_float * 16), ("T_corr", C.c_float * 16), ("converged", C.c_int), ("iterations", C.c_int),
+                ("n_points", C.c_int), ("new_keyframe", C.c_int), ("submap_changed", C.c_int), ("n_keyframes", C.c_int), ("n_submap", C.c_int)]
+
+
+HULL_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.POINTER(C.c_int), C.c_void_p)
 
 
 class NgicpError(RuntimeError):
@@ -122,6 +138,18 @@ def lib() -> C.CDLL:
     L.ngicp_filter_scan.argtypes = [vp, vp, sz, sz, fp, fp, i, fp, i, fp, C.POINTER(sz)]
     L.ngicp_scan_ingest.argtypes = [vp, vp, sz, sz, sz, i, fp, fp, i, dp, C.POINTER(sz), C.POINTER(sz)]
     L.ngicp_scan_deskew.argtypes = [vp, fp, sz, fp, i, fp, C.POINTER(sz)]
+    L.ngicp_odom_default_params.argtypes = [C.POINTER(OdomParamsC)]
+    L.ngicp_odom_default_params.restype = None
+    L.ngicp_odom_create.argtypes = [vp, C.POINTER(OdomParamsC), C.POINTER(vp)]
+    L.ngicp_odom_destroy.argtypes = [vp]
+    L.ngicp_odom_last_error.restype = C.c_char_p
+    L.ngicp_odom_last_error.argtypes = [vp]
+    L.ngicp_odom_set_hull_callbacks.argtypes = [vp, HULL_FN, HULL_FN, vp]
+    L.ngicp_odom_set_pose.argtypes = [vp, fp]
+    L.ngicp_odom_scan_begin.argtypes = [vp, vp, sz, sz, dp, C.POINTER(sz), C.POINTER(sz)]
+    L.ngicp_odom_scan_finish.argtypes = [vp, fp, sz, C.POINTER(OdomResultC), ip, i]
+    L.ngicp_odom_get_profile.argtypes = [vp, dp, C.POINTER(C.c_long), i]
+    L.ngicp_hull_planar.argtypes = [dp, i, i, C.c_double, ip]
     L.ngicp_enable_timing.argtypes = [vp, i]
     L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
     _lib = L

@@ -346,6 +346,107 @@ class OdomLoop:
             self.submap_kf_idx_prev = list(self.submap_kf_idx_curr)
 
 
+# -------------------------------------------------------------------------------------------------- the C++ loop
+class NativeOdomLoop:
+    """The same loop in C++ behind the C ABI (csrc/odom_loop.cu: ngicp_odom_*): one ctypes call before and one after the
+    caller's IMU integration per scan, instead of ~12 Python-level calls. Same decisions as OdomLoop scan by scan
+    (tests/test_gpu_odom_native.py). Spatial keyframe sets go through OdomLoop's scipy hulls as callbacks."""
+
+    def __init__(self, gicp, params: OdomParams | None = None, record_dtype=None):
+        import ctypes as C
+        from . import binding as B
+        self._C, self._B, self._L = C, B, B.lib()
+        self.gicp = gicp
+        self.p = params or OdomParams()
+        rd = np.dtype(record_dtype if record_dtype is not None else OS1_RECORD)
+        tdt, toff = rd.fields[self.p.time_field][:2]
+        cp = B.OdomParamsC()
+        self._L.ngicp_odom_default_params(C.byref(cp))
+        for f in ("crop_size", "voxel_res", "keyframe_thresh_dist", "keyframe_thresh_rot", "submap_knn", "submap_kcv", "submap_kcc",
+                  "gicp_min_num_points", "gicp_max_corr_dist"):
+            setattr(cp, f, getattr(self.p, f))
+        cp.adaptive = int(self.p.adaptive)
+        cp.time_offset_bytes = int(toff)
+        cp.time_type = {np.dtype(np.uint32): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[tdt]
+        self._o = C.c_void_p(None)
+        B.check(gicp._h, self._L.ngicp_odom_create(gicp._h, C.byref(cp), C.byref(self._o)))
+
+        def _cb(fn):
+            def call(xyz, n, alpha, out, _user):
+                try:
+                    P = np.ctypeslib.as_array(xyz, shape=(n, 3)).copy()
+                    idx = fn(P, alpha)
+                    for j, v in enumerate(idx):
+                        out[j] = int(v)
+                    return len(idx)
+                except Exception:       # noqa: BLE001 - reported by the C side as a failed callback
+                    return -1
+            return B.HULL_FN(call)
+        self._cbs = (_cb(lambda P, a: convex_hull_indices(P)), _cb(lambda P, a: concave_hull_indices(P, a)))
+        self._L.ngicp_odom_set_hull_callbacks(self._o, self._cbs[0], self._cbs[1], None)
+        self._stamps = np.empty(0, np.float64)
+        self._ids = np.empty(4096, np.int32)
+        self.n_keyframes = 0
+
+    def _check(self, rc):
+        if rc != self._B.OK:
+            msg = self._L.ngicp_odom_last_error(self._o)
+            raise self._B.NgicpError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_o", None) is not None and self._o.value:
+            self._L.ngicp_odom_destroy(self._o)
+            self._o = self._C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            if self.gicp._h.value:
+                self.close()
+        except Exception:       # noqa: BLE001
+            pass
+
+    STAGES = ("ingest", "ranges", "deskew_voxel_index", "median_params", "covariances", "align", "keyframe", "submap")
+
+    def profile(self, reset=False) -> dict:
+        """Mean host wall clock per stage of the C++ loop, milliseconds per scan."""
+        C = self._C
+        sec = (C.c_double * len(self.STAGES))()
+        n = C.c_long(0)
+        self._check(self._L.ngicp_odom_get_profile(self._o, sec, C.byref(n), int(reset)))
+        return {"scans": n.value, **{k: 1e3 * v / max(n.value, 1) for k, v in zip(self.STAGES, sec)}}
+
+    def set_pose(self, T):
+        """Initial pose of the lidar (the reference starts at the configured origin; the tests start on the truth)."""
+        t = np.ascontiguousarray(np.asarray(T, np.float32).T).reshape(16)
+        self._check(self._L.ngicp_odom_set_pose(self._o, t.ctypes.data_as(self._C.POINTER(self._C.c_float))))
+
+    def callbackPointCloud(self, records: np.ndarray, prior_frames) -> ScanResult | None:
+        C = self._C
+        rec = np.ascontiguousarray(records)
+        if len(self._stamps) < len(rec):
+            self._stamps = np.empty(len(rec), np.float64)
+        nu, nk = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._L.ngicp_odom_scan_begin(self._o, rec.ctypes.data, len(rec), rec.dtype.itemsize,
+                                                 self._stamps.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nu), C.byref(nk)))
+        fp = C.POINTER(C.c_float)
+        res = self._B.OdomResultC()
+        ids = self._ids.ctypes.data_as(C.POINTER(C.c_int))
+        if prior_frames is None or nk.value == 0:
+            rc = self._L.ngicp_odom_scan_finish(self._o, None, 0, C.byref(res), ids, len(self._ids))
+        else:
+            F = np.asarray(prior_frames(self._stamps[:nu.value]), np.float32)
+            Fc = np.ascontiguousarray(F.transpose(0, 2, 1)).reshape(-1, 16)
+            rc = self._L.ngicp_odom_scan_finish(self._o, Fc.ctypes.data_as(fp), len(Fc), C.byref(res), ids, len(self._ids))
+        self._check(rc)
+        if not res.valid:
+            return None
+        self.n_keyframes = res.n_keyframes
+        T = np.array(res.T, np.float32).reshape(4, 4).T.copy()
+        Tc = np.array(res.T_corr, np.float32).reshape(4, 4).T.copy()
+        return ScanResult(T, Tc, bool(res.converged), res.iterations, res.n_points, bool(res.new_keyframe),
+                          self._ids[:res.n_submap].tolist(), bool(res.submap_changed))
+
+
 # ---------------------------------------------------------------------------------------------- synthetic sequences
 OS1_RECORD = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), ("w", np.float32), ("intensity", np.float32),
                        ("t", np.uint32), ("pad", np.uint32, 2)])      # 32 B, dlio::Point (include/dlio/dlio.h:85-108)

@@ -146,6 +146,81 @@ def test_odom_loop_on_the_device_matches_the_loop_over_the_oracle(params, mulran
     assert max(err) < 0.02
 
 
+def _native_hull(P, concave, alpha=0.0):
+    import ctypes as C
+    from ngicp import binding as B
+    P = np.ascontiguousarray(P, np.float64)
+    out = np.empty(len(P), np.int32)
+    m = B.lib().ngicp_hull_planar(P.ctypes.data_as(C.POINTER(C.c_double)), len(P), int(concave), float(alpha), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return m if m < 0 else out[:m].tolist()
+
+
+def test_native_planar_hulls_match_the_qhull_ones():
+    """csrc/odom_loop.cu's own 2-D convex hull and alpha shape (what the C++ loop uses for planar keyframe sets) against
+    the scipy/qhull restatement of PCL's ConvexHull / ConcaveHull used by the Python loop; host code, no GPU needed."""
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(4, 120))
+        P = np.zeros((n, 3))
+        if trial % 2:       # a drive: a noisy path
+            P[:, :2] = np.cumsum(rng.normal(0, 1.0, (n, 2)) + [1.0, 0.2], 0)
+        else:
+            P[:, :2] = rng.uniform(-20, 20, (n, 2))
+        P[:, 2] = rng.normal(0, 1e-3, n)
+        R = synth.rot_from_rotvec(rng.normal(0, 0.3, 3)) if trial % 3 == 0 else np.eye(3)
+        P = (P @ R.T).astype(np.float32).astype(np.float64)
+        assert _native_hull(P, False) == odom.convex_hull_indices(P)
+        for alpha in (0.7, 2.0, 10.0):
+            assert _native_hull(P, True, alpha) == odom.concave_hull_indices(P, alpha), (trial, alpha)
+    line = np.array([[i, 2 * i, 0.0] for i in range(6)])
+    assert _native_hull(line, False) == [0, 5]
+    cube = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)] + [[0.5, 0.5, 0.5]], float)
+    assert _native_hull(cube, False) == -3                                     # spatial: the callback case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("params,mulran", [(odom.OdomParams(), False), (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), False),
+                                           (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), True)],
+                         ids=["adaptive", "dense-keyframes", "mulran-shaped"])
+def test_the_cpp_loop_makes_the_python_loops_decisions(params, mulran):
+    """ngicp_odom_* (csrc/odom_loop.cu) against OdomLoop over DeviceBackend, both on the CUDA path, same sequence: same
+    points, keyframes, submap sets, iteration counts; poses to fp32 rounding of one 4x4 product."""
+    import ngicp
+    import scenarios as S
+    scene = synth.Scene(3)
+    n, w, groups = 30, 256, (1 if mulran else 8)
+    seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups, mulran=mulran))
+    rng = np.random.default_rng(5)
+    drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
+
+    def run(make):
+        g = S.configure(ngicp.NanoGICP(0), max_corr=0.5, max_iter=32, rot_eps=0.01, trans_eps=0.01)
+        loop = make(g)
+        res = []
+        for i, (rec, Ts, block, col_t) in enumerate(seq):
+            if i == 0:
+                if isinstance(loop, odom.NativeOdomLoop):
+                    loop.set_pose(Ts[groups // 2])
+                else:
+                    loop.T = Ts[groups // 2].astype(np.float32)
+                    loop.propagateGICP()
+                res.append(loop.callbackPointCloud(rec, None))
+                continue
+            def prior(stamps, Ts=Ts, i=i):
+                g_ = np.minimum((stamps.astype(np.int64) * groups) // 100_000_000, groups - 1)
+                return np.stack([(drift[i] @ Ts[k]).astype(np.float32) for k in g_])
+            res.append(loop.callbackPointCloud(rec, prior))
+        return res
+
+    rp = run(lambda g: odom.OdomLoop(odom.DeviceBackend(g), params))
+    rn = run(lambda g: odom.NativeOdomLoop(g, params))
+    assert sum(r.new_keyframe for r in rn) >= 3
+    for a, b in zip(rn, rp):
+        assert a.n_points == b.n_points and a.new_keyframe == b.new_keyframe and a.submap == b.submap and a.submap_changed == b.submap_changed
+        assert a.iterations == b.iterations and a.converged == b.converged
+        assert np.abs(a.T - b.T).max() < 2e-6 and np.abs(a.T_corr - b.T_corr).max() < 2e-6
+
+
 def test_synthetic_sequence_is_seeded_per_scan_and_shaped_like_the_reference_point():
     """Records are the reference's 32-byte dlio::Point (include/dlio/dlio.h:85-108); every scan has its own seeded generator,
     so scan i is the same whether it is made alone, in order, or in another process; MulRan-shaped scans carry zero stamps."""
