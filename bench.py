@@ -580,17 +580,29 @@ def odom_loop_cfg4(device, seq, groups=2):
     rng = np.random.default_rng(8)
     drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
 
+    stages = []
+
     def run(backend):
         loop = odom.OdomLoop(backend, odom.OdomParams()) if backend is not None else odom.NativeOdomLoop(configure(ngicp.NanoGICP(device)), odom.OdomParams())
         ts, res = [], []
-        drive_loop(loop, seq, drift, groups, 0, n, ts, res)
+        if backend is None:           # scan by scan, to keep the stage times of every scan
+            for i in range(n):
+                drive_loop(loop, seq, drift, groups, i, i + 1, ts, res)
+                stages.append(loop.profile(reset=True))
+        else:
+            drive_loop(loop, seq, drift, groups, 0, n, ts, res)
         return loop, res, ts
 
     lg, rg, tg = run(odom.DeviceBackend(configure(ngicp.NanoGICP(device))))
     ln, rn, tn = run(None)
     both = [(a, b) for a, b in zip(rn, rg) if a is not None and b is not None]
-    cpp = {"ms_per_scan_median": 1e3 * float(np.median(tn[3:])), "ms_per_scan_mean": 1e3 * float(np.mean(tn[3:])), "scans_per_s": float(len(tn[3:]) / np.sum(tn[3:])),
-           "keyframes": ln.n_keyframes, "stage_ms_mean": ln.profile(), "scans_compared_with_python_loop": len(both),
+    cpp = {"ms_per_scan_median": 1e3 * float(np.median(tn[3:])), "ms_per_scan_mean": 1e3 * float(np.mean(tn[3:])),
+           "ms_per_scan_p99": 1e3 * float(np.percentile(tn[3:], 99)), "ms_per_scan_max": 1e3 * float(np.max(tn[3:])), "scans_per_s": float(len(tn[3:]) / np.sum(tn[3:])),
+           "keyframes": ln.n_keyframes,
+           "stage_ms_median": {k: float(np.median([st[k] for st in stages[3:] if st["scans"]])) for k in odom.NativeOdomLoop.STAGES},
+           "slowest_scans": [{"scan": int(i), "ms": 1e3 * tn[i], "new_keyframe": bool(rn[i] and rn[i].new_keyframe),
+                              "stage_ms": {k: round(stages[i][k], 3) for k in odom.NativeOdomLoop.STAGES}} for i in np.argsort(-np.array(tn))[:3] if i >= 3],
+           "scans_compared_with_python_loop": len(both),
            "same_decisions_as_python_loop": int(sum(a.new_keyframe == b.new_keyframe and a.submap == b.submap and a.iterations == b.iterations
                                                     and a.converged == b.converged and a.n_points == b.n_points for a, b in both)),
            "max_pose_diff_m": max(float(np.abs(a.T[:3, 3] - b.T[:3, 3]).max()) for a, b in both),
@@ -601,7 +613,8 @@ def odom_loop_cfg4(device, seq, groups=2):
     pairs = [(a, b) for a, b in zip(rg, ro) if a is not None and b is not None]
     steady = tg[3:]
     return {"scans": n, "points_per_scan": int(len(seq[0][0])), "path_m": float(np.linalg.norm(np.diff([s[1][0][:3, 3] for s in seq], axis=0), axis=1).sum()),
-            "ms_per_scan_median": 1e3 * float(np.median(steady)), "ms_per_scan_mean": 1e3 * float(np.mean(steady)), "scans_per_s": float(len(steady) / np.sum(steady)),
+            "ms_per_scan_median": 1e3 * float(np.median(steady)), "ms_per_scan_mean": 1e3 * float(np.mean(steady)),
+            "ms_per_scan_p99": 1e3 * float(np.percentile(steady, 99)), "ms_per_scan_max": 1e3 * float(np.max(steady)), "scans_per_s": float(len(steady) / np.sum(steady)),
             "keyframes": len(lg.keyframes), "max_submap_keyframes": max(len(r.submap) for r in rg if r is not None),
             "submap_rebuilds": int(sum(1 for r in rg if r is not None and r.submap_changed)),
             "lm_iterations_mean": float(np.mean([r.iterations + 1 for r in rg[1:] if r is not None])),

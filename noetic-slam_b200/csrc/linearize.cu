@@ -463,6 +463,9 @@ static int check_ready(Handle* h) {
 
 static int ensure_corr(Handle* h, size_t n) {
   if (h->corr_cap >= n) return NGICP_OK;
+  // cudaFree / cudaMalloc synchronise the device (and were seen to take tens to hundreds of ms in a process whose memory
+  // pool is warm): grow rarely — the voxel-filtered scans of a sequence differ by a few percent from one to the next
+  n = ((n + n / 4 + 4095) / 4096) * 4096;
   drop_speculation(h);
   if (h->corr) NGICP_CUDA(h, cudaFree(h->corr));
   if (h->corr_alt) NGICP_CUDA(h, cudaFree(h->corr_alt));
