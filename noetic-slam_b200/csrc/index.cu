@@ -266,9 +266,51 @@ __global__ void __launch_bounds__(256) table_build_kernel(const unsigned long lo
   }
 }
 
+// Scan-sized builds (levels already chosen by index_cluster_kernel). A position opens / closes d - fine cells (d = first
+// level at which it differs from a neighbour), anything from 0 to 13, and the per-position loop of table_build_kernel is
+// as slow as its longest chain of dependent find-or-inserts. Here row r < kTbRows - 1 of the grid handles the single level
+// fine + r of every position (most cells live in the finest levels), and the last row loops over the few coarser ones.
+// (Measured alternatives: one row per level for all 13 levels 22 us, warp-pooled (position, level) pairs dealt out
+// round-robin 30-40 us, the per-position loop 31 us; the kernel is bound by the latency of the atomics.)
+constexpr int kTbRows = 7;
+__device__ __forceinline__ void table_insert(CellSlot* __restrict__ table, uint32_t mask, unsigned long long k, int L, int j, bool opens, bool closes) {
+  const unsigned long long ck = cell_key(k, L);
+  uint32_t h = hash64(ck) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&table[h].key, kEmptyKey, ck);
+    if (prev == kEmptyKey || prev == ck) break;
+    h = (h + 1) & mask;
+  }
+  if (opens) table[h].start = (uint32_t)j;
+  if (closes) table[h].end = (uint32_t)(j + 1);
+}
+__global__ void __launch_bounds__(256) table_build_levels_kernel(const unsigned long long* __restrict__ keys, int n, const GridMeta* __restrict__ meta,
+                                                                 CellSlot* __restrict__ table, uint32_t mask) {
+  const int fine = meta->fine_level;
+  const int row = (int)blockIdx.y;
+  const int L0 = fine + row;
+  if (L0 > kTopLevel) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long k = keys[j];
+  const int d_open = j == 0 ? kNumLevels : diff_levels(k, keys[j - 1]);
+  const int d_close = j == n - 1 ? kNumLevels : diff_levels(k, keys[j + 1]);
+  if (row < kTbRows - 1) {
+    if (L0 < d_open || L0 < d_close) table_insert(table, mask, k, L0, j, L0 < d_open, L0 < d_close);
+  } else {
+    const int d = max(d_open, d_close);
+    for (int L = L0; L < d; L++) table_insert(table, mask, k, L, j, L < d_open, L < d_close);
+  }
+}
+
 inline int ceil_log2(unsigned int v) { int b = 0; while ((1u << b) < v) b++; return b; }
 
 }  // namespace
+}  // namespace ngicp
+
+#include "index_cluster.cuh"
+
+namespace ngicp {
 
 void free_index(Index* idx, cudaStream_t stream) {
   if (!idx) return;
@@ -319,6 +361,10 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
                s_sort = s_vals_b + align_up(sizeof(uint32_t) * (size_t)n), s_bbox = s_sort + align_up(sizeof(uint32_t) * scratch_elems),
                scratch_bytes = s_bbox + align_up(sizeof(unsigned int) * 6 * (size_t)n_seg);
   char* scratch = nullptr;
+  // scan-sized single clouds: the whole front end (bbox .. sorted points + level histogram) is one cluster kernel
+  static const int k1_cluster = [] { const char* e = std::getenv("NGICP_K1_CLUSTER"); return e ? std::atoi(e) : 1; }();
+  const ClusterShape cl_shape = (k1_cluster && n_seg == 1 && low_bit == 0) ? cluster_shape_for(n) : ClusterShape{0, 0};
+  const bool use_cluster = cl_shape.ctas > 0;
 #define IDX_CUDA(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t _e = (expr);                                                                             \
@@ -328,7 +374,7 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
     }                                                                                                    \
   } while (0)
   IDX_CUDA(dev_alloc(&idx->arena, arena_bytes, s));
-  IDX_CUDA(dev_alloc(&scratch, scratch_bytes, s));
+  if (!use_cluster) IDX_CUDA(dev_alloc(&scratch, scratch_bytes, s));
   idx->pts = reinterpret_cast<float4*>(idx->arena + o_pts);
   idx->inv = reinterpret_cast<int*>(idx->arena + o_inv);
   idx->keys = reinterpret_cast<unsigned long long*>(idx->arena + o_keys);
@@ -355,6 +401,14 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   const int tpb = 256;
   const int nb = (n + tpb - 1) / tpb;
   const int n_hist = passes * kSortRadix;
+  unsigned long long* keys_sorted = nullptr;
+  uint32_t* vals_sorted = nullptr;
+  if (use_cluster) {
+    IDX_CUDA(launch_index_cluster(d_xyz, stride, n, passes, idx->seg_origin, idx->seg_start, idx->meta, idx->keys, idx->pts, idx->inv, cl_shape,
+                                  fine ? cap / 2 + cap / 8 : cap / 2, 2, fine, h->fine_occ10, s));
+    count_launch(h);
+    keys_sorted = idx->keys;
+  } else {
   index_prep_kernel<<<(std::max(3 * n_seg, n_hist) + 255) / 256, 256, 0, s>>>(lo, hi, n_seg, sort_scratch, n_hist, n_seg == 1 ? idx->seg_start : nullptr, n);
   bbox_kernel<<<std::min(nb, n_seg == 1 ? 148 : 148 * 8), tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, lo, hi);
   count_launch(h, 2);
@@ -364,16 +418,17 @@ int build_index(Handle* h, const float* d_xyz, int stride, int n, const int64_t*
   }
   keys_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, idx->seg_start, n_seg, idx->seg_origin, idx->meta, lo, hi, keys_a, vals_a, sort_scratch, low_bit, passes);
   count_launch(h);
-  unsigned long long* keys_sorted = nullptr;
-  uint32_t* vals_sorted = nullptr;
   count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, low_bit, nbits, s, &keys_sorted, &vals_sorted, true));
   if (keys_sorted != idx->keys) {  // n == 1: nothing was sorted
     IDX_CUDA(cudaMemcpyAsync(idx->keys, keys_sorted, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     keys_sorted = idx->keys;
   }
   gather_levels_kernel<<<nb, tpb, 0, s>>>(d_xyz, stride, n, vals_sorted, keys_sorted, idx->pts, idx->inv, idx->meta);
-  table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, fine ? cap / 2 + cap / 8 : cap / 2, 2, fine, h->fine_occ10);
-  count_launch(h, 2);
+  count_launch(h);
+  }
+  if (use_cluster) table_build_levels_kernel<<<dim3(nb, kTbRows), tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask);
+  else table_build_kernel<<<nb, tpb, 0, s>>>(keys_sorted, n, idx->meta, idx->table, idx->table_mask, fine ? cap / 2 + cap / 8 : cap / 2, 2, fine, h->fine_occ10);
+  count_launch(h);
   IDX_CUDA(cudaGetLastError());
   IDX_CUDA(cudaEventCreateWithFlags(&idx->built, cudaEventDisableTiming));
   IDX_CUDA(cudaEventRecord(idx->built, s));
