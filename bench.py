@@ -660,10 +660,10 @@ def bulk_covariance_cfg3(g, scans, hbm, owned):
     out["covariance_mpts_s_device"] = n / (dev_ms * 1e-3) / 1e6
     k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
     out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"],
-                          "traffic": ncu_traffic("bulk_K3"), "traffic_note": "ncu capture of a 64-keyframe (4,194,304-point) launch, scaled by points",
+                          "traffic": ncu_traffic("bulk_K3"), "traffic_note": "ncu --set full capture of the 256-keyframe (16,777,216-point) launch, per point x this launch's points",
                           "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
     if out["roofline_K3"]["traffic"] is not None:
-        out["roofline_K3"]["traffic"] *= n / (64 * N_SCAN)
+        out["roofline_K3"]["traffic"] *= n / float(ncu_traffic("bulk_K3_points") or CFG3_KEYFRAMES * N_SCAN)
     return out
 
 
@@ -693,49 +693,11 @@ def bulk_covariance(g, scans, hbm, n_keyframes=64):
     dev_ms = out["index_ms"] + out["knn_ms"] + out["covariance_ms"]
     out["covariance_mpts_s_device"] = n / (dev_ms * 1e-3) / 1e6
     k3 = BYTES["K3_cov_per_pt"] * n / (out["covariance_ms"] * 1e-3) / 1e9
-    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"], "traffic": ncu_traffic("bulk_K3"),
+    tr = ncu_traffic("bulk_K3")
+    out["roofline_K3"] = {"bound": "hbm", "achieved": k3, "peak": hbm["gbs"], "unit": "GB/s", "frac": k3 / hbm["gbs"],
+                          "traffic": None if tr is None else tr * n / float(ncu_traffic("bulk_K3_points") or n),
                           "algorithmic_bytes_per_pt": BYTES["K3_cov_per_pt"], "peak_source": hbm["source"]}
     return out
-
-
-def odom_loop_probe(device, n_scans=24):
-    """BASELINE config 4 in miniature: a seeded OS1-64 sequence (65,536 points per scan, the sensor moving during every
-    scan) through the odom loop over the device path (ngicp/odom.py: ingest + time sort, deskew with per-stamp priors,
-    VoxelGrid, index + covariances, align, keyframe capture / transform, submap assembly — all in HBM; the keyframe and
-    submap policy on the host). Wall clock per scan, host work and the per-scan H2D of the 2 MB record buffer included."""
-    import ngicp
-    from ngicp import odom, synth
-    scene = synth.Scene(4)
-    groups = 2
-    seq = list(odom.synthetic_sequence(scene, n_scans, seed=4, step=0.4, w=1024, groups=groups))
-    rng = np.random.default_rng(8)
-    drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n_scans)]
-    g = configure(ngicp.NanoGICP(device))
-    loop = odom.OdomLoop(odom.DeviceBackend(g), odom.OdomParams())
-    ts, its, err = [], [], []
-    for i, (rec, Ts, block, col_t) in enumerate(seq):
-        t0 = time.perf_counter()
-        if i == 0:
-            if hasattr(loop, "set_pose"):
-                loop.set_pose(Ts[groups // 2])
-            else:
-                loop.T = Ts[groups // 2].astype(np.float32)
-                loop.propagateGICP()
-            r = loop.callbackPointCloud(rec, None)
-        else:
-            def prior(stamps, Ts=Ts, i=i):
-                k = np.minimum((stamps.astype(np.int64) * groups) // 100_000_000, groups - 1)
-                return (drift[i] @ Ts)[k].astype(np.float32)
-            r = loop.callbackPointCloud(rec, prior)
-        ts.append(time.perf_counter() - t0)
-        its.append(r.iterations + 1)
-        err.append(float(np.abs(r.T[:3, 3] - Ts[groups // 2][:3, 3]).max()))
-    steady = ts[3:]
-    return {"odom_loop": {"scans": n_scans, "points_per_scan": int(len(seq[0][0])), "ms_per_scan_median": 1e3 * float(np.median(steady)),
-                          "ms_per_scan_mean": 1e3 * float(np.mean(steady)), "scans_per_s": float(len(steady) / np.sum(steady)),
-                          "keyframes": len(loop.keyframes), "submap_keyframes": len(loop.submap_kf_idx_curr),
-                          "lm_iterations_mean": float(np.mean(its[1:])), "max_abs_position_error_m": max(err[1:]),
-                          "note": "wall clock per callbackPointCloud incl. host policy, H2D of the raw 32-byte records, D2H of the deskewed cloud"}}
 
 
 def multi_sequence_probe(g, tgt, m4, d_scans, device, sequences=4, steps=24):

@@ -20,6 +20,7 @@
 #include "internal.h"
 #include "linearize.cuh"
 #include "radix_sort.cuh"
+#include "cluster_sort.cuh"
 
 namespace ngicp {
 
@@ -422,7 +423,14 @@ int voxel_grid_device(Handle* h, const float* d_in, int stride, int n, const flo
   count_launch(h, 3);
   unsigned long long* keys_sorted = nullptr;
   uint32_t* vals_sorted = nullptr;
-  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  cudaError_t cl_err = cudaSuccess;
+  if (cluster_sort_identity(keys_a, n, nbits, keys_b, vals_b, s, &cl_err)) {      // scan-sized: one cluster kernel (cluster_sort.cuh)
+    NGICP_CUDA(h, cl_err);
+    count_launch(h);
+    keys_sorted = keys_b; vals_sorted = vals_b;
+  } else {
+    count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  }
   const int nb = (n + kFiltThreads - 1) / kFiltThreads;
   unsigned int* d_sums = nullptr;
   NGICP_CUDA(h, dev_alloc(&d_sums, (size_t)nb + 1, s));
@@ -549,7 +557,14 @@ int ngicp_scan_ingest(ngicp_handle* p, const void* points, size_t n, size_t stri
   count_launch(h);
   unsigned long long* keys_sorted = nullptr;
   uint32_t* vals_sorted = nullptr;
-  count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, (int)n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  cudaError_t cl_err = cudaSuccess;
+  if (cluster_sort_identity(keys_a, (int)n, nbits, keys_b, vals_b, s, &cl_err)) {   // scan-sized, <= 47 key bits: one cluster kernel
+    NGICP_CUDA(h, cl_err);
+    count_launch(h);
+    keys_sorted = keys_b; vals_sorted = vals_b;
+  } else {
+    count_launch(h, radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, sort_scratch, (int)n, 0, nbits, s, &keys_sorted, &vals_sorted, true));
+  }
   const unsigned long long seq = ++h->seq;
   zero_u32_kernel<<<1, 1, 0, s>>>(d_sums + nb + 1);
   ingest_count_kernel<<<nb, kFiltThreads, 0, s>>>(keys_sorted, (int)n, d_sums, d_sums + nb + 1);

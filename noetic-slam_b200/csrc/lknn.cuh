@@ -59,7 +59,10 @@ static __device__ unsigned int g_leaf_dbg[64][24];
 #define LEAF_CLK_ADD(i, t0) do { } while (0)
 #endif
 
-constexpr int kLeafHeavy = 768;    // first passes that would stage more candidates than this are split by child cell and re-queued
+#ifndef NGICP_LEAF_HEAVY
+#define NGICP_LEAF_HEAVY 768
+#endif
+constexpr int kLeafHeavy = NGICP_LEAF_HEAVY;    // first passes that would stage more candidates than this are split by child cell and re-queued
 constexpr int kLeafPend = 8;       // pending distances per lane between two merges
 
 // one work item of the search (8 bytes)

@@ -12,6 +12,18 @@ tgt, bounds, scans = bench.make_workload(0)
 g = bench.configure(ngicp.NanoGICP(0))
 _, m4, _ = g.batchCovariances(tgt, bounds, want_mat4=True)
 g.setInputTarget(tgt); g.setTargetCovariances(m4)
+import ctypes
+try:
+    _rt = ctypes.CDLL("libcudart.so")
+except OSError:
+    import torch  # noqa: F401  (loads the CUDA runtime it ships)
+    _rt = ctypes.CDLL([m for m in open("/proc/self/maps").read().split() if "libcudart" in m][0])
+for i in range(2):          # warm-up outside the profiled range
+    g.setInputSource(scans[i % len(scans)].copy()); g.calculateSourceCovariances(); T = g.align()
+g.synchronize()
+_rt.cudaProfilerStart()
 for i in range(steps):
     g.setInputSource(scans[i % len(scans)].copy()); g.calculateSourceCovariances(); T = g.align()
+g.synchronize()
+_rt.cudaProfilerStop()
 print("iters", g.nr_iterations_, "launches", g.timings()["kernel_launches"])
