@@ -106,19 +106,29 @@ def configure(g):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md). 100 ms period: every query takes
+    the driver's global lock, and at -lms 10 the sampler of rank 0 stalled kernel launches of the OTHER ranks for 8-12 ms
+    at a time (measured at N = 8: the cfg-3 index build 0.72 ms on some ranks, 8-12 ms on others; gone without the sampler)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, cores=None):
         self.index = index
         self.rows = []
         self.proc = None
+        self.cores = set(cores) if cores else None     # where nvidia-smi and the reader thread may run (not the launching thread's core)
+
+    def _move(self):
+        if self.cores:
+            try:
+                os.sched_setaffinity(0, self.cores)
+            except OSError:
+                pass
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, preexec_fn=self._move)
             threading.Thread(target=self._read, daemon=True).start()
             t0 = time.time()
             while not self.rows and time.time() - t0 < 3.0:   # nvidia-smi needs a moment to come up
@@ -128,6 +138,7 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        self._move()
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
@@ -185,7 +196,7 @@ def run_reference(args, rank):
 def workload_config(world):
     return {"workload": "cfg2 scan-to-submap GICP: 65,536-pt synthetic OS1-64 scan vs 1,000,000-pt keyframe submap (40 keyframes, covariance reuse), "
                         "k=16, max_corr 0.5 m, max_iter 32, eps 0.01/0.01; step = setInputSource + calculateSourceCovariances + align",
-            "sequences": world, "parallelism": f"independent sequences x{world} (no collective)",
+            "sequences": world, "parallelism": f"independent sequences x{world} (no collective); every rank registers the same seeded scans against its own resident copy of the submap",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -199,6 +210,25 @@ def pin_rank_to_cores(local_rank, world):
         mine = cores[local_rank * per:(local_rank + 1) * per] or cores
         os.sched_setaffinity(0, mine)
         return mine
+    except (AttributeError, OSError):
+        return None
+
+
+def dedicate_core_to_main_thread(cores):
+    """The launching thread gets the first core of the rank's slice to itself: every helper thread that exists by now (CUDA,
+    NCCL proxy / watchdog, BLAS pools) is moved to the other cores. A 2-3 ms preemption of the launch -> poll loop is a
+    quarter of a 20-step timed region."""
+    try:
+        if not cores or len(cores) < 2:
+            return
+        main = threading.get_native_id()
+        rest = set(cores[1:])
+        for t in os.listdir("/proc/self/task"):
+            tid = int(t)
+            try:
+                os.sched_setaffinity(tid, {cores[0]} if tid == main else rest)
+            except OSError:
+                pass
     except (AttributeError, OSError):
         return None
 
@@ -242,7 +272,11 @@ def run_gpu(args, rank, local_rank, world):
     cores = pin_rank_to_cores(local_rank, world)
     # ---- host data first: the sequence generators fork worker processes, which must happen before CUDA is initialised
     t_gen = time.time()
-    tgt, bounds, scans = make_workload(rank)
+    # every rank gets the SAME seeded workload (its own resident copy of the submap, the same eight scans in the same order):
+    # per-GPU work is then exactly fixed as N grows, and the sharded legs (cfg 3 keyframes, cfg 5 sequences) partition one
+    # global job that is the same at every N. (With per-rank seeds the max-over-ranks time is set by the hardest sequence:
+    # 0.92 of linear at N = 8 from heterogeneity alone.)
+    tgt, bounds, scans = make_workload(0)
     owned_seq = sharding.units_for_rank(CFG5_SEQUENCES, rank, world)
     specs = [(100 + k, CFG5_SCANS, 0.4, 1, True) for k in owned_seq]          # cfg 5: MulRan-shaped (t = 0), one deskew group
     with_cfg4 = world == 1 and CFG4_SCANS > 0
@@ -291,11 +325,12 @@ def run_gpu(args, rank, local_rank, world):
 
     W, K = max(3, args.warmup), args.steps     # never fewer than three warm-up steps (timing rules)
     # ---- value: device-resident input, CUDA events on the handle's stream
-    sampler = ClockSampler(local_rank) if rank == 0 else None      # one sampler per job, not one per rank
+    sampler = ClockSampler(local_rank, cores[1:] if cores and len(cores) > 1 else None) if rank == 0 and os.environ.get("NGICP_BENCH_SAMPLER", "1") != "0" else None      # one sampler per job, not one per rank
     iters = []
     g.timings(reset=True)
     launches0 = 0
     dts = []
+    dedicate_core_to_main_thread(cores)
     for i in range(W + K):
         if i == W:
             if sampler:
@@ -319,9 +354,9 @@ def run_gpu(args, rank, local_rank, world):
     t_max, units = reduce_job(t_local, float(K))
     value = units / t_max
     # per-rank spread of the step time (separates jitter from a systematic slow-down at N > 1)
-    step_ms = [1e3 * float(np.median(dts[W:])), 1e3 * float(np.min(dts[W:])), 1e3 * float(np.max(dts[W:]))]
+    step_ms = [1e3 * float(np.median(dts[W:])), 1e3 * float(np.min(dts[W:])), 1e3 * float(np.max(dts[W:])), float(np.argmax(dts[W:]))]
     if world > 1:
-        allv = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+        allv = torch.zeros(world, 4, dtype=torch.float64, device=dev)
         allv[rank] = torch.tensor(step_ms, dtype=torch.float64)
         dist.all_reduce(allv)
         per_rank = allv.cpu().numpy().tolist()
@@ -353,7 +388,11 @@ def run_gpu(args, rank, local_rank, world):
 
     e2e_value, e2e_ms = e2e_loop("pinned")
     e2e_pg_value, e2e_pg_ms = e2e_loop("pageable")
-    clocks = sampler.stop() if sampler else None     # sampled across the timed regions (device-resident loop and host-buffer loops)
+    if cores:
+        try:
+            os.sched_setaffinity(0, cores)     # the legs below start their own threads: back to the rank's whole slice
+        except OSError:
+            pass
 
     # ---- BASELINE config 3 across the ranks (strong scaling): 256 keyframes x 65,536 points in total, keyframe i on rank i mod N
     hbm = peak_hbm()
@@ -361,9 +400,18 @@ def run_gpu(args, rank, local_rank, world):
     bulk = bulk_covariance_cfg3(g, scans, hbm, owned_kf)
     shard_ms = bulk["index_ms"] + bulk["knn_ms"] + bulk["covariance_ms"]
     b_t, b_pts = reduce_job(shard_ms * 1e-3, float(bulk["points"]))
+    clocks = sampler.stop() if sampler else None     # sampled across the timed regions (device-resident loop, host-buffer loops, cfg-3 build)
     k3_t, _ = reduce_job(bulk["covariance_ms"] * 1e-3, 0.0)
     k2_t, _ = reduce_job(bulk["knn_ms"] * 1e-3, 0.0)
-    bulk["all_ranks"] = {"ranks": world, "keyframes": CFG3_KEYFRAMES, "points": int(b_pts), "covariance_build_mpts_s": b_pts / b_t / 1e6,
+    shard = [bulk["index_ms"], bulk["knn_ms"], bulk["covariance_ms"]]
+    if world > 1:
+        allb = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+        allb[rank] = torch.tensor(shard, dtype=torch.float64)
+        dist.all_reduce(allb)
+        shard_per_rank = allb.cpu().numpy().round(4).tolist()
+    else:
+        shard_per_rank = [[round(v, 4) for v in shard]]
+    bulk["all_ranks"] = {"per_rank_index_knn_cov_ms": shard_per_rank, "ranks": world, "keyframes": CFG3_KEYFRAMES, "points": int(b_pts), "covariance_build_mpts_s": b_pts / b_t / 1e6,
                          "build_ms_max_over_ranks": 1e3 * b_t, "knn_ms_max_over_ranks": 1e3 * k2_t, "K3_only_gpts_s": b_pts / k3_t / 1e9,
                          "scaling": "strong (16,777,216 points in total, keyframe i -> rank i mod N)"}
 
@@ -444,7 +492,7 @@ def run_gpu(args, rank, local_rank, world):
         "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(world),
         "ms_per_align_step": 1e3 * t_max / K, "lm_iterations_per_scan": mean_it,
-        "per_rank_step_ms_median_min_max": per_rank,
+        "per_rank_step_ms_median_min_max_argmax": per_rank,
         "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": N_SCAN * 32,
                 "host_buffer": "page-locked 32-byte AoS scan, copied as it is (cudaMemcpyAsync); the call returns when the copy has landed",
                 "d2h_bytes_per_step": d2h, "d2h_note": "host-mapped result rows the kernels write (counted from the row sizes, not metered)"},

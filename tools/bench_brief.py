@@ -15,4 +15,4 @@ print("bulk.all_ranks", b.get("all_ranks"))
 print("multi_sequence_8", d.get("multi_sequence_8"))
 print("odom_loop_cfg4", d.get("odom_loop_cfg4"))
 print("cpu", d.get("cpu_baseline"))
-print("per_rank", d.get("per_rank_step_ms_median_min_max"), "clocks", d.get("clocks"))
+print("per_rank", d.get("per_rank_step_ms_median_min_max_argmax"), "clocks", d.get("clocks"))
