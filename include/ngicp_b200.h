@@ -134,7 +134,9 @@ int ngicp_clear(ngicp_handle* h, int which);       /* clearSource / clearTarget,
 int ngicp_compute_covariances(ngicp_handle* h, int which, float* density);
 /* getSourceCovariances / getTargetCovariances (nano_gicp.h:106-112): n x 16 doubles, original order */
 int ngicp_get_covariances(ngicp_handle* h, int which, double* out_4x4, size_t n);
-/* setSourceCovariances / setTargetCovariances (nano_gicp.cc:164-171) */
+/* setSourceCovariances / setTargetCovariances (nano_gicp.cc:164-171). The device keeps the upper-left 3x3 block as six
+ * fp32 values (xx, xy, xz, yy, yz, zz): covariances handed in as fp64 are rounded to fp32 (the reference keeps fp64;
+ * its own covariances are fp64 images of fp32 point differences, for which the tests measure < 1e-7 absolute). */
 int ngicp_set_covariances(ngicp_handle* h, int which, const double* in_4x4, size_t n);
 int ngicp_has_covariances(const ngicp_handle* h, int which, size_t* n);
 

@@ -141,12 +141,23 @@ class NanoGICP:
         self.nr_iterations_ = 0
         self.final_transformation_ = np.eye(4, dtype=np.float32)
 
-    def __del__(self):
+    def close(self):
+        """Release the device object now. The trees this object handed out (source_kdtree_ / target_kdtree_) keep a
+        reference to it, which is a cycle: without close() the device memory waits for Python's cyclic collector."""
         if getattr(self, "_h", None) and self._h.value:
+            for t in (self.source_kdtree_, self.target_kdtree_):
+                if t is not None and getattr(t, "_owner", None) is self:
+                    t.__del__()            # drop the index reference while the handle is alive
             self.source_kdtree_ = None
             self.target_kdtree_ = None
             self._L.ngicp_destroy(self._h)
             self._h = C.c_void_p(None)
+
+    def __enter__(self): return self
+    def __exit__(self, *exc): self.close()
+
+    def __del__(self):
+        self.close()
 
     def _push(self):
         B.check(self._h, self._L.ngicp_set_params(self._h, C.byref(self._p)))
