@@ -215,18 +215,18 @@ def pin_rank_to_cores(local_rank, world):
 
 
 def dedicate_core_to_main_thread(cores):
-    """The launching thread gets the first core of the rank's slice to itself: every helper thread that exists by now (CUDA,
+    """The launching thread gets one core of the rank's slice to itself: every helper thread that exists by now (CUDA,
     NCCL proxy / watchdog, BLAS pools) is moved to the other cores. A 2-3 ms preemption of the launch -> poll loop is a
     quarter of a 20-step timed region."""
     try:
         if not cores or len(cores) < 2:
             return
         main = threading.get_native_id()
-        rest = set(cores[1:])
+        rest = set(cores[:-1])          # the LAST core of the slice: core 0 of a box takes its interrupts and housekeeping
         for t in os.listdir("/proc/self/task"):
             tid = int(t)
             try:
-                os.sched_setaffinity(tid, {cores[0]} if tid == main else rest)
+                os.sched_setaffinity(tid, {cores[-1]} if tid == main else rest)
             except OSError:
                 pass
     except (AttributeError, OSError):
@@ -325,7 +325,7 @@ def run_gpu(args, rank, local_rank, world):
 
     W, K = max(3, args.warmup), args.steps     # never fewer than three warm-up steps (timing rules)
     # ---- value: device-resident input, CUDA events on the handle's stream
-    sampler = ClockSampler(local_rank, cores[1:] if cores and len(cores) > 1 else None) if rank == 0 and os.environ.get("NGICP_BENCH_SAMPLER", "1") != "0" else None      # one sampler per job, not one per rank
+    sampler = ClockSampler(local_rank, cores[:-1] if cores and len(cores) > 1 else None) if rank == 0 and os.environ.get("NGICP_BENCH_SAMPLER", "1") != "0" else None      # one sampler per job, not one per rank
     iters = []
     g.timings(reset=True)
     launches0 = 0

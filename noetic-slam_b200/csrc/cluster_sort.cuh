@@ -42,8 +42,9 @@ struct ClusterSmem {
   uint32_t half[kSortRadix];                            // keys of the digit in warps 16..31
   uint32_t lower[kSortRadix];                           // keys of the digit in warps 0..15
   uint32_t scan_tmp[32];
-  unsigned int box_lo[3], box_hi[3];                    // CTA 0: cluster-wide bounding box (order-preserving integer images)
-  unsigned int lvl[16];                                 // CTA 0: cluster-wide level histogram
+  unsigned int box_lo[3], box_hi[3];                    // this CTA's bounding box (order-preserving integer images)
+  unsigned int gbox_lo[3], gbox_hi[3];                  // the cluster's bounding box, folded by every CTA for itself
+  unsigned int lvl[16];                                 // this CTA's level histogram
 };
 
 // exclusive scan of one value per thread over the block (all 1024 threads call it)
@@ -97,9 +98,12 @@ __device__ __forceinline__ void cluster_lsd_passes(ClusterSmem<kClItems>& sm, cg
     // rank inside the warp's run (kept in registers) while counting: the leader of every digit group reads the counter,
     // adds the group size, and hands the old value to the group
     uint32_t lrank[kClItems];
+    unsigned mm[kClItems];
+#pragma unroll
+    for (int r = 0; r < kClItems; r++) mm[r] = __match_any_sync(0xffffffffu, dig[r]);     // independent: all in flight together
 #pragma unroll
     for (int r = 0; r < kClItems; r++) {
-      const unsigned m = __match_any_sync(0xffffffffu, dig[r]);
+      const unsigned m = mm[r];
       const int leader = __ffs(m) - 1;
       uint32_t old = 0;
       if (dig[r] < kSortRadix && lane == leader) {

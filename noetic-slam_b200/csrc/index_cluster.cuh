@@ -23,13 +23,14 @@ __global__ void __launch_bounds__(kClThreads, 1) index_cluster_kernel(const floa
   const int c = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  ClusterSmem* sm0 = cluster.map_shared_rank(&sm, 0);
   const int first = c * kClTile;                         // global position of this CTA's first record
   const int mine = max(0, min(kClTile, n - first));      // records this CTA owns (in every pass: positions are dense)
 
-  // ---- bounding box: registers -> warp -> CTA 0 (DSMEM atomics) ----
-  if (c == 0 && threadIdx.x < 3) { sm.box_lo[threadIdx.x] = 0xffffffffu; sm.box_hi[threadIdx.x] = 0u; }
-  if (c == 0 && threadIdx.x < 16) sm.lvl[threadIdx.x] = 0u;
+  // ---- bounding box: registers -> warp -> this CTA's shared memory (local atomics); after one cluster barrier every CTA
+  //      folds the boxes of all CTAs itself (6 x ncta DSMEM loads), so nothing funnels through one CTA's shared memory ----
+  if (threadIdx.x < 3) { sm.box_lo[threadIdx.x] = 0xffffffffu; sm.box_hi[threadIdx.x] = 0u; sm.gbox_lo[threadIdx.x] = 0xffffffffu; sm.gbox_hi[threadIdx.x] = 0u; }
+  if (threadIdx.x < 16) sm.lvl[threadIdx.x] = 0u;
+  __syncthreads();
   float px[kClItems], py[kClItems], pz[kClItems];
   unsigned int l[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, u[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -53,16 +54,21 @@ __global__ void __launch_bounds__(kClThreads, 1) index_cluster_kernel(const floa
       u[a] = max(u[a], __shfl_xor_sync(0xffffffffu, u[a], off));
     }
   }
-  cluster.sync();                                        // CTA 0's box is initialised
   if (lane < 3) {
     const unsigned int ml = lane == 0 ? l[0] : (lane == 1 ? l[1] : l[2]), mu = lane == 0 ? u[0] : (lane == 1 ? u[1] : u[2]);
-    atomicMin(&sm0->box_lo[lane], ml);
-    atomicMax(&sm0->box_hi[lane], mu);
+    atomicMin(&sm.box_lo[lane], ml);
+    atomicMax(&sm.box_hi[lane], mu);
   }
-  cluster.sync();
+  cluster.sync();                                        // every CTA's box is final (and every CTA of the cluster is resident)
+  if (threadIdx.x < 3 * ncta) {
+    const ClusterSmem* rs = cluster.map_shared_rank(&sm, threadIdx.x / 3);
+    atomicMin(&sm.gbox_lo[threadIdx.x % 3], rs->box_lo[threadIdx.x % 3]);
+    atomicMax(&sm.gbox_hi[threadIdx.x % 3], rs->box_hi[threadIdx.x % 3]);
+  }
+  __syncthreads();
   // ---- grid parameters (every thread from the same six words) and voxel keys, exactly as keys_kernel ----
-  const float4 o = make_float4(ord2f(sm0->box_lo[0]), ord2f(sm0->box_lo[1]), ord2f(sm0->box_lo[2]), 0.f);
-  const float h0 = cell_size_for(fmaxf(ord2f(sm0->box_hi[0]) - o.x, fmaxf(ord2f(sm0->box_hi[1]) - o.y, ord2f(sm0->box_hi[2]) - o.z)));
+  const float4 o = make_float4(ord2f(sm.gbox_lo[0]), ord2f(sm.gbox_lo[1]), ord2f(sm.gbox_lo[2]), 0.f);
+  const float h0 = cell_size_for(fmaxf(ord2f(sm.gbox_hi[0]) - o.x, fmaxf(ord2f(sm.gbox_hi[1]) - o.y, ord2f(sm.gbox_hi[2]) - o.z)));
   const float inv_h0 = 1.0f / h0;
   if (c == 0 && threadIdx.x == 0) { seg_origin[0] = o; write_meta(meta, h0); seg_start[0] = 0; seg_start[1] = n; }
   unsigned long long rec[kClItems];
@@ -102,10 +108,15 @@ __global__ void __launch_bounds__(kClThreads, 1) index_cluster_kernel(const floa
 #pragma unroll
   for (int r = 0; r < kClItems; r++) {
     const unsigned m = __match_any_sync(0xffffffffu, lv[r]);
-    if (lv[r] && lane == __ffs(m) - 1) atomicAdd(&sm0->lvl[lv[r]], (unsigned int)__popc(m));
+    if (lv[r] && lane == __ffs(m) - 1) atomicAdd(&sm.lvl[lv[r]], (unsigned int)__popc(m));     // this CTA's own histogram
+  }
+  cluster.sync();                                        // every CTA's level histogram is final
+  if (c == 0 && threadIdx.x < 16) {
+    unsigned int t = 0;
+    for (int cc = 0; cc < ncta; cc++) t += cluster.map_shared_rank(&sm, cc)->lvl[threadIdx.x];
+    meta->level_hist[threadIdx.x] = t;
   }
   cluster.sync();                                        // nobody leaves while its shared memory may still be read
-  if (c == 0 && threadIdx.x < 16) meta->level_hist[threadIdx.x] = sm.lvl[threadIdx.x];
   if (c == 0) {
     __syncthreads();
     if (threadIdx.x == 0) {                              // the levels the table will hold (table_build_levels_kernel reads them)
