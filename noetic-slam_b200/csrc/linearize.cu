@@ -486,7 +486,16 @@ static int ensure_corr(Handle* h, size_t n) {
 static int search_blocks_for(int n, int lpq) {
   const int items = (n * lpq + 31) / 32;                         // one warp-sized work item per 32/lpq points
   const int want = (items + (kLinThreads / 32) - 1) / (kLinThreads / 32);
-  return std::max(1, std::min(want, 148 * 6));
+  // exactly the blocks that are resident at once (the warps stride over the queries): a partial second wave of blocks
+  // would run its whole share on a nearly empty machine
+  static const int per_sm = [] {
+    if (const char* e = std::getenv("NGICP_K4_BLOCKS_PER_SM")) return std::max(1, std::atoi(e));
+    int a = 0, b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, correspond_fast_kernel<true>, kLinThreads, 0) != cudaSuccess) a = 5;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, correspond_fast_kernel<false>, kLinThreads, 0) != cudaSuccess) b = 5;
+    return std::max(1, std::min(a, b));
+  }();
+  return std::max(1, std::min(want, 148 * per_sm));
 }
 
 // K4 = correspondence search + fused linearisation over n_scans source segments (n_scans = 1: the reference's
