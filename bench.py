@@ -201,34 +201,62 @@ def workload_config(world):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def physical_cores(cpus):
+    """The allowed logical CPUs grouped by physical core (hyper-thread siblings together), from sysfs."""
+    groups, seen = [], set()
+    for c in sorted(cpus):
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    sib.update(range(int(a), int(b or a) + 1))
+        except (OSError, ValueError):
+            pass
+        sib &= set(cpus)
+        seen |= sib
+        groups.append(sorted(sib))
+    return groups
+
+
+_RANK_CORES = {"groups": None}
+
+
 def pin_rank_to_cores(local_rank, world):
-    """Disjoint host cores per rank: the LM loop is ~12 launch -> poll round trips per scan, and eight unpinned processes
-    (plus a clock sampler) on the same cores turn into step-time jitter at N = 8."""
+    """Disjoint PHYSICAL cores per rank: the LM loop is ~10 launch -> poll round trips per scan, and eight unpinned processes
+    on the same cores — or two polling threads on the two hyper-threads of one core — turn into step-time loss at N > 1."""
     try:
-        cores = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cores) // max(world, 1))
-        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
-        os.sched_setaffinity(0, mine)
-        return mine
+        groups = physical_cores(os.sched_getaffinity(0))
+        per = max(1, len(groups) // max(world, 1))
+        mine = groups[local_rank * per:(local_rank + 1) * per] or groups
+        _RANK_CORES["groups"] = mine
+        cpus = sorted(c for g in mine for c in g)
+        os.sched_setaffinity(0, cpus)
+        return cpus
     except (AttributeError, OSError):
         return None
 
 
 def dedicate_core_to_main_thread(cores):
-    """The launching thread gets one core of the rank's slice to itself: every helper thread that exists by now (CUDA,
-    NCCL proxy / watchdog, BLAS pools) is moved to the other cores. A 2-3 ms preemption of the launch -> poll loop is a
-    quarter of a 20-step timed region."""
+    """The launching thread gets one physical core of the rank's slice to itself (the last one: core 0 of a box takes its
+    interrupts and housekeeping); every helper thread that exists by now (CUDA, NCCL proxy / watchdog, BLAS pools) is moved
+    to the other cores, the hyper-thread sibling of the launching thread's CPU stays idle. A 2-3 ms preemption of the
+    launch -> poll loop is a quarter of a 20-step timed region."""
     try:
-        if not cores or len(cores) < 2:
-            return
+        groups = _RANK_CORES["groups"]
+        if not groups or len(groups) < 2:
+            return None
         main = threading.get_native_id()
-        rest = set(cores[:-1])          # the LAST core of the slice: core 0 of a box takes its interrupts and housekeeping
+        rest = {c for g in groups[:-1] for c in g}
         for t in os.listdir("/proc/self/task"):
             tid = int(t)
             try:
-                os.sched_setaffinity(tid, {cores[-1]} if tid == main else rest)
+                os.sched_setaffinity(tid, {groups[-1][0]} if tid == main else rest)
             except OSError:
                 pass
+        return sorted(rest)
     except (AttributeError, OSError):
         return None
 
@@ -325,7 +353,7 @@ def run_gpu(args, rank, local_rank, world):
 
     W, K = max(3, args.warmup), args.steps     # never fewer than three warm-up steps (timing rules)
     # ---- value: device-resident input, CUDA events on the handle's stream
-    sampler = ClockSampler(local_rank, cores[:-1] if cores and len(cores) > 1 else None) if rank == 0 and os.environ.get("NGICP_BENCH_SAMPLER", "1") != "0" else None      # one sampler per job, not one per rank
+    sampler = ClockSampler(local_rank, [c for g in (_RANK_CORES["groups"] or [])[:-1] for c in g] or None) if rank == 0 and os.environ.get("NGICP_BENCH_SAMPLER", "1") != "0" else None      # one sampler per job, not one per rank
     iters = []
     g.timings(reset=True)
     launches0 = 0
