@@ -106,9 +106,9 @@ def configure(g):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md). 100 ms period: every query takes
-    the driver's global lock, and at -lms 10 the sampler of rank 0 stalled kernel launches of the OTHER ranks for 8-12 ms
-    at a time (measured at N = 8: the cfg-3 index build 0.72 ms on some ranks, 8-12 ms on others; gone without the sampler)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md; its period, 200 ms). Every query
+    takes driver-wide locks: at -lms 10 the sampler of rank 0 stalled kernel launches of the OTHER ranks for 8-12 ms at a
+    time (measured at N = 8: the cfg-3 index build 0.72 ms on some ranks, 8-12 ms on others; gone without the sampler)."""
 
     def __init__(self, index: int, cores=None):
         self.index = index
@@ -127,7 +127,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, preexec_fn=self._move)
             threading.Thread(target=self._read, daemon=True).start()
             t0 = time.time()
