@@ -52,3 +52,34 @@ def test_product_never_imports_the_oracle():
     for f in (ROOT / "noetic-slam_b200").rglob("*"):
         if f.suffix in (".py", ".cu", ".cuh", ".h", ".cc") and f.is_file():
             assert not pat.search(f.read_text()), f
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_python_mirror(tmp_path):
+    """include/ngicp_b200.h must compile as C (the boundary is a C ABI, not a C++ one), and the ctypes mirrors of its
+    structs (ngicp/binding.py) must have the C compiler's sizes and field offsets."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from ngicp import binding as B
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"ngicp_params": B.Params, "ngicp_timings": B.Timings, "ngicp_odom_params": B.OdomParamsC, "ngicp_odom_result": B.OdomResultC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ngicp_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        cls = structs[name]
+        assert int(size) == C.sizeof(cls), name
+        assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
