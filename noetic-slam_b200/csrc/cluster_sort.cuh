@@ -110,6 +110,7 @@ __device__ __forceinline__ void cluster_lsd_passes(ClusterSmem<kClItems>& sm, cg
         old = sm.warp_cnt[warp][dig[r]];
         sm.warp_cnt[warp][dig[r]] = (unsigned short)(old + __popc(m));
       }
+      __syncwarp();                                      // the next round's leaders (other lanes) read what this round's wrote
       old = __shfl_sync(0xffffffffu, old, leader);
       lrank[r] = old + __popc(m & lt_mask);
     }
