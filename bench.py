@@ -256,6 +256,10 @@ def dedicate_core_to_main_thread(cores):
                 os.sched_setaffinity(tid, {groups[-1][0]} if tid == main else rest)
             except OSError:
                 pass
+        try:
+            os.setpriority(os.PRIO_PROCESS, main, -20)      # the spinning launch thread should not lose its core to a waking daemon
+        except (OSError, AttributeError):
+            pass
         return sorted(rest)
     except (AttributeError, OSError):
         return None
@@ -419,7 +423,8 @@ def run_gpu(args, rank, local_rank, world):
     if cores:
         try:
             os.sched_setaffinity(0, cores)     # the legs below start their own threads: back to the rank's whole slice
-        except OSError:
+            os.setpriority(os.PRIO_PROCESS, threading.get_native_id(), 0)
+        except (OSError, AttributeError):
             pass
 
     # ---- BASELINE config 3 across the ranks (strong scaling): 256 keyframes x 65,536 points in total, keyframe i on rank i mod N
