@@ -362,7 +362,8 @@ def run_gpu(args, rank, local_rank, world):
     g.timings(reset=True)
     launches0 = 0
     dts = []
-    dedicate_core_to_main_thread(cores)
+    if os.environ.get("NGICP_BENCH_DEDICATE", "1") != "0":
+        dedicate_core_to_main_thread(cores)
     for i in range(W + K):
         if i == W:
             if sampler:
