@@ -7,7 +7,7 @@
 
 namespace ngicp {
 
-// 9-bit digits: the 27 key bits of a single cloud's index (levels >= 3) sort in three passes instead of four. One thread
+// 9-bit digits: the 36 key bits of a single cloud's index sort in four passes (32-bit VoxelGrid indices too). One thread
 // per digit in the count / scan steps, so a tile is 512 threads.
 constexpr int kSortRadixBits = 9;
 constexpr int kSortRadix = 1 << kSortRadixBits;
