@@ -83,3 +83,22 @@ def test_header_is_plain_c_and_struct_layouts_match_the_python_mirror(tmp_path):
         cls = structs[name]
         assert int(size) == C.sizeof(cls), name
         assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
+
+
+def test_odom_loop_defaults_are_the_reference_yaml_values_and_null_arguments_are_refused():
+    """ngicp_odom_default_params = reference src/dlio/cfg/params.yaml:43-59 + cfg/dlio.yaml:17; the entry points refuse NULL
+    handles with NGICP_ERR_INVALID instead of touching the device (no GPU needed)."""
+    import ctypes as C
+    L = B.lib()
+    p = B.OdomParamsC()
+    L.ngicp_odom_default_params(C.byref(p))
+    assert (p.crop_size, p.voxel_res, p.keyframe_thresh_dist, p.keyframe_thresh_rot) == (1.0, 0.25, 1.0, 45.0)
+    assert (p.submap_knn, p.submap_kcv, p.submap_kcc, p.gicp_min_num_points, p.adaptive) == (10, 10, 10, 64, 1)
+    assert abs(p.gicp_max_corr_dist - 0.5) < 1e-7 and (p.time_offset_bytes, p.time_type) == (20, 0)     # dlio::Point `t`
+    out = C.c_void_p(None)
+    assert L.ngicp_odom_create(None, C.byref(p), C.byref(out)) == B.ERR_INVALID and not out.value
+    n = C.c_size_t(0)
+    assert L.ngicp_odom_scan_begin(None, None, 0, 32, None, C.byref(n), None) == B.ERR_INVALID
+    res = B.OdomResultC()
+    assert L.ngicp_odom_scan_finish(None, None, 0, C.byref(res), None, 0) == B.ERR_INVALID
+    assert L.ngicp_odom_destroy(None) == B.OK
