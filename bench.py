@@ -362,6 +362,16 @@ def run_gpu(args, rank, local_rank, world):
     g.timings(reset=True)
     launches0 = 0
     dts = []
+    if world > 1:
+        # NCCL sets its connections up lazily, inside the first collectives, and tidies up (buffer registration, proxy
+        # threads, device allocations and frees — the latter synchronise this rank's GPU) for a few milliseconds afterwards:
+        # take that out of the way now, so that the barrier in front of the timed region is a steady-state collective
+        for _ in range(3):
+            dist.barrier()
+            warm_t = torch.zeros(8, dtype=torch.float64, device=dev)
+            dist.all_reduce(warm_t)
+            dist.all_reduce(warm_t, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
     if os.environ.get("NGICP_BENCH_DEDICATE", "1") != "0":
         dedicate_core_to_main_thread(cores)
     for i in range(W + K):
