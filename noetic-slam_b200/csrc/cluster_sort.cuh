@@ -28,6 +28,7 @@ namespace cg = cooperative_groups;
 constexpr int kClThreads = 1024;
 constexpr int kClValBits = 17;                          // original index < 131,072 = 16 CTAs x 8192
 constexpr int kClMaxCtas = 16;
+constexpr int kClMaxDevices = 64;
 constexpr int kClMaxPoints = kClMaxCtas * kClThreads * 8;
 constexpr unsigned long long kClValMask = (1ull << kClValBits) - 1ull;
 
@@ -253,8 +254,11 @@ inline cudaError_t cluster_launch(void (*fn)(Args...), ClusterShape shape, size_
 inline bool cluster_sort_identity(const unsigned long long* keys_in, int n, int nbits, unsigned long long* keys_out, uint32_t* vals_out, cudaStream_t s,
                                   cudaError_t* err) {
   static const int enabled = [] { const char* e = std::getenv("NGICP_SORT_CLUSTER"); return e ? std::atoi(e) : 1; }();
-  static int ok4[kClMaxCtas + 1] = {0}, ok8[kClMaxCtas + 1] = {0};
+  static int ok4_dev[kClMaxDevices][kClMaxCtas + 1] = {{0}}, ok8_dev[kClMaxDevices][kClMaxCtas + 1] = {{0}};   // function attributes are per device
   *err = cudaSuccess;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kClMaxDevices) return false;
+  int *ok4 = ok4_dev[dev], *ok8 = ok8_dev[dev];
   if (!enabled || n < 2 || n > kClMaxPoints || nbits < 1 || nbits > 64 - kClValBits) return false;
   const int passes = (nbits + kSortRadixBits - 1) / kSortRadixBits;
   const int c4 = (n + kClThreads * 4 - 1) / (kClThreads * 4), c8 = (n + kClThreads * 8 - 1) / (kClThreads * 8);

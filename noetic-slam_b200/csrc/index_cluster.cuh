@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(kClThreads, 1) index_cluster_kernel(const floa
 }
 
 inline ClusterShape cluster_shape_for(int n) {
-  static int ok4[kClMaxCtas + 1] = {0}, ok8[kClMaxCtas + 1] = {0};
+  static int ok4_dev[kClMaxDevices][kClMaxCtas + 1] = {{0}}, ok8_dev[kClMaxDevices][kClMaxCtas + 1] = {{0}};   // function attributes are per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kClMaxDevices) return {0, 0};
+  int *ok4 = ok4_dev[dev], *ok8 = ok8_dev[dev];
   if (n < 2 || n > kClMaxPoints) return {0, 0};
   const int c4 = (n + kClThreads * 4 - 1) / (kClThreads * 4), c8 = (n + kClThreads * 8 - 1) / (kClThreads * 8);
   if (c4 <= kClMaxCtas && cluster_launchable(index_cluster_kernel<4>, c4, sizeof(ClusterSmem<4>), ok4)) return {c4, 4};
