@@ -236,9 +236,9 @@ int ngicp_scan_deskew(ngicp_handle* h, const float* frames16, size_t n_frames, c
  *                covariances, align against the current submap, pose propagation, keyframe decision, keyframe capture /
  *                transform and submap re-assembly, all without the scan or a covariance leaving HBM.
  * res->valid == 0: the scan was dropped (empty after the crop, or <= gicp_min_num_points points, odom.cc:764-767).
- * Planar keyframe sets (pcl::ConvexHull's 2-D case) are handled inside; for spatial sets the caller installs the two hull
- * callbacks (indices of the points on the hull of n xyz doubles; return the count or < 0), else scan_finish fails with
- * NGICP_ERR_UNSUPPORTED. One ngicp_odom owns its handle's source, target and keyframes for its lifetime. */
+ * Planar keyframe sets (pcl::ConvexHull's 2-D case) and spatial ones are handled inside (2-D / 3-D hull and alpha shape);
+ * a caller that wants PCL's own hulls for spatial sets installs the two hull callbacks (indices of the points on the hull
+ * of n xyz doubles; return the count or < 0). A degenerate spatial set without callbacks fails with NGICP_ERR_UNSUPPORTED. One ngicp_odom owns its handle's source, target and keyframes for its lifetime. */
 typedef struct ngicp_odom ngicp_odom;
 typedef struct ngicp_odom_params {
   float crop_size;             /* preprocessing/cropBoxFilter/size   (cfg/params.yaml:43) */
@@ -276,6 +276,10 @@ int ngicp_odom_get_profile(ngicp_odom* o, double seconds[NGICP_ODOM_STAGES], lon
 /* the planar hull used inside (exported for tests): indices (ascending) of the points on the convex hull (concave == 0)
  * or on the alpha shape of n xyz doubles; returns the count, -3 when the set is spatial (callback case), -1 on bad input */
 int ngicp_hull_planar(const double* xyz, int n, int concave, double alpha, int* out_indices);
+/* the spatial counterpart, used when no hull callbacks are installed: extreme points of the 3-D convex hull (incremental
+ * insertion) or vertices of the 3-D alpha shape (Delaunay tetrahedra with circumradius <= alpha, faces of exactly one kept
+ * tetrahedron); returns the count, -2 for a degenerate set (fewer than 4 points, all coplanar, numerical trouble) */
+int ngicp_hull_spatial(const double* xyz, int n, int concave, double alpha, int* out_indices);
 int ngicp_odom_scan_finish(ngicp_odom* o, const float* frames16, size_t n_frames, ngicp_odom_result* res, int* submap_ids, int submap_cap);
 
 /* ---- timing hooks used by bench.py (device time of the last call's stages, milliseconds) ------- */

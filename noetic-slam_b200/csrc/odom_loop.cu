@@ -215,12 +215,45 @@ void delaunay_2d(const std::vector<P2>& Q, std::vector<Tri>& tris) {
 
 // vertices of the 2-D alpha shape: Delaunay triangles with circumradius <= alpha, boundary = edges of exactly one kept
 // triangle (pcl::ConcaveHull with setAlpha, odom.cc:1496-1512)
-void concave_hull_2d(const std::vector<P2>& Q, double alpha, std::vector<int>& out) {
+// A Delaunay simplex with its circumradius: the alpha shape for ANY alpha is read off a list of these (the triangulation
+// depends on the points only, so the loop keeps the list between scans and re-filters it when only alpha moved).
+struct Simplex { int v[4]; int nv; double radius; };
+
+// boundary vertices of the alpha shape: simplices with circumradius <= alpha are kept, the shape's boundary is made of the
+// faces that belong to exactly one kept simplex (pcl::ConcaveHull with setAlpha, odom.cc:1496-1512)
+void alpha_boundary(const std::vector<Simplex>& S, double alpha, std::vector<int>& out) {
   out.clear();
+  struct Face { int v[3]; bool operator<(const Face& o) const { return v[0] != o.v[0] ? v[0] < o.v[0] : (v[1] != o.v[1] ? v[1] < o.v[1] : v[2] < o.v[2]); }
+                bool operator==(const Face& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2]; } };
+  std::vector<Face> faces;
+  int fv = 0;
+  for (const Simplex& t : S) {
+    if (t.radius > alpha) continue;
+    fv = t.nv - 1;
+    for (int skip = 0; skip < t.nv; skip++) {
+      Face f = {{-1, -1, -1}};
+      int k = 0;
+      for (int q = 0; q < t.nv; q++) if (q != skip) f.v[k++] = t.v[q];
+      std::sort(f.v, f.v + fv);
+      faces.push_back(f);
+    }
+  }
+  std::sort(faces.begin(), faces.end());
+  for (size_t i = 0; i < faces.size();) {
+    size_t j = i;
+    while (j < faces.size() && faces[j] == faces[i]) j++;
+    if (j - i == 1) for (int k = 0; k < fv; k++) out.push_back(faces[i].v[k]);
+    i = j;
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+void alpha_simplices_2d(const std::vector<P2>& Q, std::vector<Simplex>& S) {
+  S.clear();
   if (Q.size() < 3) return;
   std::vector<Tri> tris;
   delaunay_2d(Q, tris);
-  std::vector<std::pair<int, int>> edges;
   for (const Tri& t : tris) {
     const P2 &v0 = Q[t.v[0]], &v1 = Q[t.v[1]], &v2 = Q[t.v[2]];
     // circumcentre: 2 (V_i - V_0) . c = |V_i|^2 - |V_0|^2
@@ -229,18 +262,162 @@ void concave_hull_2d(const std::vector<P2>& Q, double alpha, std::vector<int>& o
     const double det = a11 * a22 - a12 * a21;
     if (!(std::fabs(det) > 1e-300)) continue;
     const double cx = (r1 * a22 - a12 * r2) / det, cy = (a11 * r2 - r1 * a21) / det;
-    if (std::sqrt((cx - v0.x) * (cx - v0.x) + (cy - v0.y) * (cy - v0.y)) > alpha) continue;
-    for (int e = 0; e < 3; e++) edges.push_back({std::min(t.v[e], t.v[(e + 1) % 3]), std::max(t.v[e], t.v[(e + 1) % 3])});
+    S.push_back({{t.v[0], t.v[1], t.v[2], -1}, 3, std::sqrt((cx - v0.x) * (cx - v0.x) + (cy - v0.y) * (cy - v0.y))});
   }
-  std::sort(edges.begin(), edges.end());
-  for (size_t i = 0; i < edges.size();) {
-    size_t j = i;
-    while (j < edges.size() && edges[j] == edges[i]) j++;
-    if (j - i == 1) { out.push_back(edges[i].first); out.push_back(edges[i].second); }
-    i = j;
+}
+void concave_hull_2d(const std::vector<P2>& Q, double alpha, std::vector<int>& out) {
+  std::vector<Simplex> S;
+  alpha_simplices_2d(Q, S);
+  alpha_boundary(S, alpha, out);
+}
+
+// ---- spatial keyframe sets (a sensor that also moves vertically): 3-D convex hull and 3-D alpha shape ----
+struct P3 { double x, y, z; };
+inline P3 sub(const P3& a, const P3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline P3 cross3(const P3& a, const P3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double dot3(const P3& a, const P3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// signed volume x 6 of (a, b, c, d): > 0 when d is on the side of the plane (a, b, c) its normal (b-a) x (c-a) points to
+inline double orient3(const P3& a, const P3& b, const P3& c, const P3& d) { return dot3(cross3(sub(b, a), sub(c, a)), sub(d, a)); }
+
+// Extreme points of the 3-D convex hull by incremental insertion (faces keep outward normals; a point that sees no face
+// beyond a relative tolerance is inside or on the hull and is not a vertex — what qhull reports). false: degenerate input.
+bool convex_hull_3d(const std::vector<P3>& Q, std::vector<int>& out) {
+  out.clear();
+  const int n = (int)Q.size();
+  if (n < 4) return false;
+  double ext = 0;
+  for (const P3& p : Q) ext = std::max(ext, std::max(std::fabs(p.x - Q[0].x), std::max(std::fabs(p.y - Q[0].y), std::fabs(p.z - Q[0].z))));
+  const double eps = 1e-10 * ext * ext * ext + 1e-300;
+  // initial tetrahedron: two far points, the point farthest from their line, the point farthest from that plane
+  int i0 = 0, i1 = 0, i2 = -1, i3 = -1;
+  for (int i = 1; i < n; i++) if (Q[i].x < Q[i0].x || (Q[i].x == Q[i0].x && (Q[i].y < Q[i0].y || (Q[i].y == Q[i0].y && Q[i].z < Q[i0].z)))) i0 = i;
+  double best = -1;
+  for (int i = 0; i < n; i++) { const P3 d = sub(Q[i], Q[i0]); const double v = dot3(d, d); if (v > best) { best = v; i1 = i; } }
+  best = -1;
+  for (int i = 0; i < n; i++) { const P3 c = cross3(sub(Q[i1], Q[i0]), sub(Q[i], Q[i0])); const double v = dot3(c, c); if (v > best) { best = v; i2 = i; } }
+  best = -1;
+  for (int i = 0; i < n; i++) { const double v = std::fabs(orient3(Q[i0], Q[i1], Q[i2], Q[i])); if (v > best) { best = v; i3 = i; } }
+  if (i2 < 0 || i3 < 0 || best <= eps) return false;
+  struct Face { int a, b, c; bool alive; };
+  std::vector<Face> F;
+  auto add_face = [&](int a, int b, int c, int inside) {      // oriented so that `inside` is behind it
+    if (orient3(Q[a], Q[b], Q[c], Q[inside]) > 0) std::swap(b, c);
+    F.push_back({a, b, c, true});
+  };
+  add_face(i0, i1, i2, i3); add_face(i0, i1, i3, i2); add_face(i0, i2, i3, i1); add_face(i1, i2, i3, i0);
+  const P3 centre = {(Q[i0].x + Q[i1].x + Q[i2].x + Q[i3].x) / 4, (Q[i0].y + Q[i1].y + Q[i2].y + Q[i3].y) / 4, (Q[i0].z + Q[i1].z + Q[i2].z + Q[i3].z) / 4};
+  for (int p = 0; p < n; p++) {
+    if (p == i0 || p == i1 || p == i2 || p == i3) continue;
+    std::vector<int> vis;
+    for (int f = 0; f < (int)F.size(); f++)
+      if (F[f].alive && orient3(Q[F[f].a], Q[F[f].b], Q[F[f].c], Q[p]) > eps) vis.push_back(f);
+    if (vis.empty()) continue;
+    // horizon = directed edges of visible faces whose reverse is not an edge of a visible face
+    std::vector<std::pair<int, int>> edges;
+    for (int f : vis) { edges.push_back({F[f].a, F[f].b}); edges.push_back({F[f].b, F[f].c}); edges.push_back({F[f].c, F[f].a}); F[f].alive = false; }
+    for (size_t e = 0; e < edges.size(); e++) {
+      bool shared = false;
+      for (size_t g = 0; g < edges.size(); g++) if (edges[g].first == edges[e].second && edges[g].second == edges[e].first) { shared = true; break; }
+      if (!shared) {
+        int a = edges[e].first, b = edges[e].second, c = p;
+        // keep the interior reference point behind the new face
+        const double o = dot3(cross3(sub(Q[b], Q[a]), sub(Q[c], Q[a])), sub(centre, Q[a]));
+        if (o > 0) std::swap(a, b);
+        F.push_back({a, b, c, true});
+      }
+    }
   }
+  for (const Face& f : F) if (f.alive) { out.push_back(f.a); out.push_back(f.b); out.push_back(f.c); }
   std::sort(out.begin(), out.end());
   out.erase(std::unique(out.begin(), out.end()), out.end());
+  return true;
+}
+
+// 3-D Delaunay (Bowyer-Watson over a super-tetrahedron; keyframe counts are in the hundreds), tetrahedra as index quads
+struct Tet { int v[4]; };
+bool in_circumsphere(const P3& a, const P3& b, const P3& c, const P3& d, const P3& p) {
+  const P3 A = sub(a, p), B = sub(b, p), C = sub(c, p), D = sub(d, p);
+  const double a2 = dot3(A, A), b2 = dot3(B, B), c2 = dot3(C, C), d2 = dot3(D, D);
+  // 4x4 determinant | A a2 ; B b2 ; C c2 ; D d2 |, expanded along the last column
+  const double det = -a2 * dot3(B, cross3(C, D)) + b2 * dot3(A, cross3(C, D)) - c2 * dot3(A, cross3(B, D)) + d2 * dot3(A, cross3(B, C));
+  const double o = orient3(a, b, c, d);
+  return o > 0 ? det < 0 : det > 0;
+}
+bool delaunay_3d(const std::vector<P3>& Q, std::vector<Tet>& tets) {
+  const int n = (int)Q.size();
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (const P3& p : Q) { lo[0] = std::min(lo[0], p.x); lo[1] = std::min(lo[1], p.y); lo[2] = std::min(lo[2], p.z); hi[0] = std::max(hi[0], p.x); hi[1] = std::max(hi[1], p.y); hi[2] = std::max(hi[2], p.z); }
+  const double d = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2])) + 1.0;
+  const P3 m = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+  std::vector<P3> pts = Q;
+  const double S = 1e3 * d;
+  pts.push_back({m.x - S, m.y - S, m.z - S});
+  pts.push_back({m.x + S, m.y - S, m.z - S});
+  pts.push_back({m.x, m.y + S, m.z - S});
+  pts.push_back({m.x, m.y, m.z + S});
+  tets.clear();
+  tets.push_back({{n, n + 1, n + 2, n + 3}});
+  struct Tri3 { int a, b, c; };
+  for (int i = 0; i < n; i++) {
+    std::vector<Tri3> faces;
+    std::vector<Tet> keep;
+    for (const Tet& t : tets) {
+      if (in_circumsphere(pts[t.v[0]], pts[t.v[1]], pts[t.v[2]], pts[t.v[3]], pts[i])) {
+        for (int s = 0; s < 4; s++) {
+          int f[3], k = 0;
+          for (int q = 0; q < 4; q++) if (q != s) f[k++] = t.v[q];
+          std::sort(f, f + 3);
+          faces.push_back({f[0], f[1], f[2]});
+        }
+      } else keep.push_back(t);
+    }
+    if (faces.empty()) return false;                       // the point is in no circumsphere: numerical trouble
+    for (size_t a = 0; a < faces.size(); a++) {
+      int cnt = 0;
+      for (size_t b = 0; b < faces.size(); b++) if (faces[a].a == faces[b].a && faces[a].b == faces[b].b && faces[a].c == faces[b].c) cnt++;
+      if (cnt == 1) {
+        if (std::fabs(orient3(pts[faces[a].a], pts[faces[a].b], pts[faces[a].c], pts[i])) <= 0.0) return false;   // flat tetrahedron
+        keep.push_back({{faces[a].a, faces[a].b, faces[a].c, i}});
+      }
+    }
+    tets.swap(keep);
+  }
+  std::vector<Tet> real;
+  for (const Tet& t : tets) if (t.v[0] < n && t.v[1] < n && t.v[2] < n && t.v[3] < n) real.push_back(t);
+  tets.swap(real);
+  return true;
+}
+
+// the 3-D Delaunay tetrahedra with their circumradii (false: numerical trouble, see delaunay_3d)
+bool alpha_simplices_3d(const std::vector<P3>& Q, std::vector<Simplex>& S) {
+  S.clear();
+  if (Q.size() < 4) return true;
+  std::vector<Tet> tets;
+  if (!delaunay_3d(Q, tets)) return false;
+  for (const Tet& t : tets) {
+    const P3 &v0 = Q[t.v[0]];
+    double A[3][3], r[3];
+    for (int i = 0; i < 3; i++) {
+      const P3& vi = Q[t.v[i + 1]];
+      A[i][0] = 2 * (vi.x - v0.x); A[i][1] = 2 * (vi.y - v0.y); A[i][2] = 2 * (vi.z - v0.z);
+      r[i] = dot3(vi, vi) - dot3(v0, v0);
+    }
+    const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) + A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    if (!(std::fabs(det) > 1e-300)) continue;
+    const double cx = (r[0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (r[1] * A[2][2] - A[1][2] * r[2]) + A[0][2] * (r[1] * A[2][1] - A[1][1] * r[2])) / det;
+    const double cy = (A[0][0] * (r[1] * A[2][2] - A[1][2] * r[2]) - r[0] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) + A[0][2] * (A[1][0] * r[2] - r[1] * A[2][0])) / det;
+    const double cz = (A[0][0] * (A[1][1] * r[2] - r[1] * A[2][1]) - A[0][1] * (A[1][0] * r[2] - r[1] * A[2][0]) + r[0] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) / det;
+    const P3 dc = {cx - v0.x, cy - v0.y, cz - v0.z};
+    S.push_back({{t.v[0], t.v[1], t.v[2], t.v[3]}, 4, std::sqrt(dot3(dc, dc))});
+  }
+  return true;
+}
+// vertices of the 3-D alpha shape (the same rule as concave_hull_2d one dimension up)
+bool concave_hull_3d(const std::vector<P3>& Q, double alpha, std::vector<int>& out) {
+  std::vector<Simplex> S;
+  if (!alpha_simplices_3d(Q, S)) { out.clear(); return false; }
+  alpha_boundary(S, alpha, out);
+  return true;
 }
 
 }  // namespace
@@ -270,6 +447,12 @@ struct ngicp_odom {
   size_t pack_cap = 0;
   ngicp_hull_fn convex_cb = nullptr, concave_cb = nullptr;
   void* cb_user = nullptr;
+  // hulls of the first hull_n keyframes (their positions never change): the convex hull and the Delaunay simplices are
+  // rebuilt only when a keyframe has been added; the alpha shape is re-read from the simplices every scan (alpha adapts)
+  int hull_n = -1, hull_dim = 0;
+  bool hull_ok = false;
+  std::vector<int> hull_convex;
+  std::vector<Simplex> hull_simplices;
   std::string err;
   double prof[NGICP_ODOM_STAGES] = {0};     // host wall clock per stage, seconds, summed over scans
   long prof_scans = 0;
@@ -297,25 +480,42 @@ void propagate(ngicp_odom* o) {
 
 int hull_indices(ngicp_odom* o, bool concave, std::vector<int>& out) {
   const int n = o->num_processed;
-  std::vector<double> P(3 * (size_t)n);
-  for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) P[3 * i + a] = (double)o->keyframes[i].p[a];
-  int drop;
-  const int dim = hull_dimension(P, n, drop);
-  if (dim == 3) {
-    ngicp_hull_fn cb = concave ? o->concave_cb : o->convex_cb;
-    if (!cb) { o->err = "odom loop: spatial (non-planar) keyframe set and no hull callback installed"; return NGICP_ERR_UNSUPPORTED; }
+  if (o->hull_n != n) {
+    std::vector<double> P(3 * (size_t)n);
+    for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) P[3 * i + a] = (double)o->keyframes[i].p[a];
+    int drop;
+    o->hull_dim = hull_dimension(P, n, drop);
+    o->hull_n = n;
+    o->hull_ok = true;
+    o->hull_convex.clear();
+    o->hull_simplices.clear();
+    if (o->hull_dim == 3) {
+      if (!o->convex_cb || !o->concave_cb) {      // no caller-supplied hulls (e.g. PCL's): the native 3-D convex hull / alpha shape
+        std::vector<P3> Q3(n);
+        for (int i = 0; i < n; i++) Q3[i] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+        o->hull_ok = convex_hull_3d(Q3, o->hull_convex) && alpha_simplices_3d(Q3, o->hull_simplices);
+      }
+    } else {
+      std::vector<P2> Q(n);
+      const int ax = drop == 0 ? 1 : 0, ay = drop == 2 ? 1 : 2;
+      for (int i = 0; i < n; i++) Q[i] = {P[3 * i + ax], P[3 * i + ay]};
+      convex_hull_2d(Q, o->hull_convex);
+      alpha_simplices_2d(Q, o->hull_simplices);
+    }
+  }
+  if (o->hull_dim == 3 && o->convex_cb && o->concave_cb) {
+    std::vector<double> P(3 * (size_t)n);
+    for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) P[3 * i + a] = (double)o->keyframes[i].p[a];
     std::vector<int> buf(n);
-    const int m = cb(P.data(), n, concave ? o->concave_alpha : 0.0, buf.data(), o->cb_user);
+    const int m = (concave ? o->concave_cb : o->convex_cb)(P.data(), n, concave ? o->concave_alpha : 0.0, buf.data(), o->cb_user);
     if (m < 0) { o->err = "odom loop: hull callback failed"; return NGICP_ERR_INVALID; }
     out.assign(buf.begin(), buf.begin() + m);
     std::sort(out.begin(), out.end());
     return NGICP_OK;
   }
-  std::vector<P2> Q(n);
-  const int ax = drop == 0 ? 1 : 0, ay = drop == 2 ? 1 : 2;
-  for (int i = 0; i < n; i++) Q[i] = {P[3 * i + ax], P[3 * i + ay]};
-  if (concave) concave_hull_2d(Q, o->concave_alpha, out);
-  else convex_hull_2d(Q, out);
+  if (!o->hull_ok) { o->err = "odom loop: degenerate spatial keyframe set (install hull callbacks)"; return NGICP_ERR_UNSUPPORTED; }
+  if (concave) alpha_boundary(o->hull_simplices, o->concave_alpha, out);
+  else out = o->hull_convex;
   return NGICP_OK;
 }
 
@@ -417,6 +617,16 @@ int ngicp_hull_planar(const double* xyz, int n, int concave, double alpha, int* 
   return (int)out.size();
 }
 
+int ngicp_hull_spatial(const double* xyz, int n, int concave, double alpha, int* out_indices) {
+  if (!xyz || n <= 0 || !out_indices) return -1;
+  std::vector<P3> Q(n);
+  for (int i = 0; i < n; i++) Q[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  std::vector<int> out;
+  if (!(concave ? concave_hull_3d(Q, alpha, out) : convex_hull_3d(Q, out))) return -2;
+  std::copy(out.begin(), out.end(), out_indices);
+  return (int)out.size();
+}
+
 void ngicp_odom_default_params(ngicp_odom_params* p) {
   if (!p) return;
   p->crop_size = 1.0f; p->voxel_res = 0.25f; p->keyframe_thresh_dist = 1.0f; p->keyframe_thresh_rot = 45.0f;      // cfg/params.yaml:43-49
@@ -452,6 +662,7 @@ const char* ngicp_odom_last_error(const ngicp_odom* o) { return o ? (o->err.empt
 int ngicp_odom_set_hull_callbacks(ngicp_odom* o, ngicp_hull_fn convex, ngicp_hull_fn concave, void* user) {
   if (!o) return NGICP_ERR_INVALID;
   o->convex_cb = convex; o->concave_cb = concave; o->cb_user = user;
+  o->hull_n = -1;       // the cached hulls were made by the other route
   return NGICP_OK;
 }
 

@@ -29,7 +29,7 @@ SYMBOLS = [
     "ngicp_keyframe_capture", "ngicp_keyframe_transform", "ngicp_keyframe_size", "ngicp_keyframe_release", "ngicp_keyframe_download",
     "ngicp_submap_assemble", "ngicp_filter_scan", "ngicp_scan_ingest", "ngicp_scan_deskew",
     "ngicp_odom_default_params", "ngicp_odom_create", "ngicp_odom_destroy", "ngicp_odom_last_error", "ngicp_odom_set_hull_callbacks",
-    "ngicp_odom_set_pose", "ngicp_odom_get_profile", "ngicp_odom_scan_begin", "ngicp_odom_scan_finish", "ngicp_hull_planar",
+    "ngicp_odom_set_pose", "ngicp_odom_get_profile", "ngicp_odom_scan_begin", "ngicp_odom_scan_finish", "ngicp_hull_planar", "ngicp_hull_spatial",
     "ngicp_enable_timing", "ngicp_get_timings",
 ]
 
@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
     L.ngicp_odom_scan_finish.argtypes = [vp, fp, sz, C.POINTER(OdomResultC), ip, i]
     L.ngicp_odom_get_profile.argtypes = [vp, dp, C.POINTER(C.c_long), i]
     L.ngicp_hull_planar.argtypes = [dp, i, i, C.c_double, ip]
+    L.ngicp_hull_spatial.argtypes = [dp, i, i, C.c_double, ip]
     L.ngicp_enable_timing.argtypes = [vp, i]
     L.ngicp_get_timings.argtypes = [vp, C.POINTER(Timings), i]
     _lib = L

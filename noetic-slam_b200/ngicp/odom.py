@@ -350,9 +350,9 @@ class OdomLoop:
 class NativeOdomLoop:
     """The same loop in C++ behind the C ABI (csrc/odom_loop.cu: ngicp_odom_*): one ctypes call before and one after the
     caller's IMU integration per scan, instead of ~12 Python-level calls. Same decisions as OdomLoop scan by scan
-    (tests/test_gpu_odom_native.py). Spatial keyframe sets go through OdomLoop's scipy hulls as callbacks."""
+    (tests/test_odom.py). Hulls are native (2-D for planar keyframe sets, 3-D otherwise)."""
 
-    def __init__(self, gicp, params: OdomParams | None = None, record_dtype=None):
+    def __init__(self, gicp, params: OdomParams | None = None, record_dtype=None, hull_callbacks: bool = False):
         import ctypes as C
         from . import binding as B
         self._C, self._B, self._L = C, B, B.lib()
@@ -382,8 +382,12 @@ class NativeOdomLoop:
                 except Exception:       # noqa: BLE001 - reported by the C side as a failed callback
                     return -1
             return B.HULL_FN(call)
-        self._cbs = (_cb(lambda P, a: convex_hull_indices(P)), _cb(lambda P, a: concave_hull_indices(P, a)))
-        self._L.ngicp_odom_set_hull_callbacks(self._o, self._cbs[0], self._cbs[1], None)
+        # planar AND spatial keyframe sets are handled natively; hull_callbacks=True routes spatial sets through the qhull
+        # restatement above instead (what a C++ caller would do with pcl::ConvexHull / pcl::ConcaveHull)
+        self._cbs = None
+        if hull_callbacks:
+            self._cbs = (_cb(lambda P, a: convex_hull_indices(P)), _cb(lambda P, a: concave_hull_indices(P, a)))
+            self._L.ngicp_odom_set_hull_callbacks(self._o, self._cbs[0], self._cbs[1], None)
         self._stamps = np.empty(0, np.float64)
         self._ids = np.empty(4096, np.int32)
         self.n_keyframes = 0

@@ -178,18 +178,71 @@ def test_native_planar_hulls_match_the_qhull_ones():
     assert _native_hull(cube, False) == -3                                     # spatial: the callback case
 
 
+def _native_hull_3d(P, concave, alpha=0.0):
+    import ctypes as C
+    from ngicp import binding as B
+    P = np.ascontiguousarray(P, np.float64)
+    out = np.empty(len(P), np.int32)
+    m = B.lib().ngicp_hull_spatial(P.ctypes.data_as(C.POINTER(C.c_double)), len(P), int(concave), float(alpha), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return m if m < 0 else out[:m].tolist()
+
+
+def test_native_spatial_hulls_match_the_qhull_ones():
+    """The 3-D convex hull (incremental insertion) and 3-D alpha shape (Bowyer-Watson Delaunay) the C++ loop uses for spatial
+    keyframe sets when no callbacks are installed, against the scipy/qhull restatement of PCL's hulls; host code, no GPU."""
+    rng = np.random.default_rng(1)
+    for trial in range(45):
+        n = int(rng.integers(5, 160))
+        if trial % 3 == 0:
+            P = rng.uniform(-20, 20, (n, 3))
+        elif trial % 3 == 1:
+            P = np.cumsum(rng.normal(0, 1.0, (n, 3)) + [1.0, 0.2, 0.3], 0)          # a flight path
+        else:
+            P = rng.normal(0, 5, (n, 3)) * [1, 1, 0.3]
+        P = P.astype(np.float32).astype(np.float64)
+        assert odom._hull_dimension(P)[0] == 3
+        assert _native_hull_3d(P, False) == odom.convex_hull_indices(P), trial
+        for alpha in (1.0, 3.0, 8.0, 50.0):
+            assert _native_hull_3d(P, True, alpha) == odom.concave_hull_indices(P, alpha), (trial, alpha)
+    cube = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)] + [[0.5, 0.5, 0.5]], float)
+    assert _native_hull_3d(cube, False) == list(range(8)) == _native_hull_3d(cube, True, 2.0)      # eight cospherical corners
+    flat = np.concatenate([rng.uniform(-5, 5, (30, 2)), np.zeros((30, 1))], 1)
+    assert _native_hull_3d(flat, False) == -2                                  # coplanar: the planar route's business
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("params,mulran", [(odom.OdomParams(), False), (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), False),
                                            (odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), True)],
                          ids=["adaptive", "dense-keyframes", "mulran-shaped"])
 def test_the_cpp_loop_makes_the_python_loops_decisions(params, mulran):
+    _cpp_vs_python_loop(params, mulran, climb=0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("callbacks", [False, True], ids=["native-3d-hulls", "qhull-callbacks"])
+def test_the_cpp_loop_on_a_climbing_trajectory_uses_spatial_hulls(callbacks):
+    """The sensor also moves up and down (0.9 m amplitude): the keyframe set becomes spatial, PCL's dimension switch picks
+    3-D hulls, and the C++ loop — with its native 3-D hull / alpha shape, and with the qhull restatement installed as
+    callbacks — still makes the Python loop's decisions."""
+    _cpp_vs_python_loop(odom.OdomParams(adaptive=False, keyframe_thresh_dist=0.5), False, climb=0.9, callbacks=callbacks)
+
+
+def _cpp_vs_python_loop(params, mulran, climb, callbacks=False):
     """ngicp_odom_* (csrc/odom_loop.cu) against OdomLoop over DeviceBackend, both on the CUDA path, same sequence: same
     points, keyframes, submap sets, iteration counts; poses to fp32 rounding of one 4x4 product."""
     import ngicp
     import scenarios as S
     scene = synth.Scene(3)
     n, w, groups = 30, 256, (1 if mulran else 8)
-    seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups, mulran=mulran))
+    if climb:
+        poses = odom.synthetic_poses(scene, n, seed=3, step=0.3)
+        poses = [P.copy() for P in poses]
+        for i, P in enumerate(poses):
+            P[2, 3] += climb * np.sin(0.45 * max(i - 1, 0))                     # at rest during scan 0, then up and down
+            # (a steady climb along a nearly straight path is still a PLANAR keyframe set for PCL's dimension switch)
+        seq = [odom.synthetic_scan(scene, poses, i, 3, w, groups, mulran) for i in range(n)]
+    else:
+        seq = list(odom.synthetic_sequence(scene, n, seed=3, step=0.3, w=w, groups=groups, mulran=mulran))
     rng = np.random.default_rng(5)
     drift = [synth.random_se3(rng, 0.03, 0.3) for _ in range(n)]
 
@@ -213,8 +266,11 @@ def test_the_cpp_loop_makes_the_python_loops_decisions(params, mulran):
         return res
 
     rp = run(lambda g: odom.OdomLoop(odom.DeviceBackend(g), params))
-    rn = run(lambda g: odom.NativeOdomLoop(g, params))
+    rn = run(lambda g: odom.NativeOdomLoop(g, params, hull_callbacks=callbacks))
     assert sum(r.new_keyframe for r in rn) >= 3
+    if climb:
+        kf = np.array([r.T[:3, 3] for r in rp if r is not None and r.new_keyframe])
+        assert len(kf) >= 5 and odom._hull_dimension(kf.astype(np.float64))[0] == 3       # the spatial route was taken
     for a, b in zip(rn, rp):
         assert a.n_points == b.n_points and a.new_keyframe == b.new_keyframe and a.submap == b.submap and a.submap_changed == b.submap_changed
         assert a.iterations == b.iterations and a.converged == b.converged
