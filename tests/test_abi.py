@@ -102,3 +102,47 @@ def test_odom_loop_defaults_are_the_reference_yaml_values_and_null_arguments_are
     res = B.OdomResultC()
     assert L.ngicp_odom_scan_finish(None, None, 0, C.byref(res), None, 0) == B.ERR_INVALID
     assert L.ngicp_odom_destroy(None) == B.OK
+
+
+def test_a_plain_c_program_links_and_calls_the_library(tmp_path):
+    """The boundary from the consumer's side: a C99 program that includes the header, links libngicp_b200.so and calls the
+    entry points that need no device (version, defaults, the host-side hull) — then asks for a handle and, without a B200,
+    must get NGICP_ERR_NO_DEVICE and an error text instead of a CPU fallback."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ngicp_b200.h"
+int main(void) {
+  ngicp_params p;
+  ngicp_odom_params op;
+  ngicp_default_params(&p);
+  ngicp_odom_default_params(&op);
+  const double sq[] = {0, 0, 0, 4, 0, 0, 4, 4, 0, 0, 4, 0, 2, 2, 0, 1, 3, 0};
+  int idx[6];
+  const int m = ngicp_hull_planar(sq, 6, 0, 0.0, idx);
+  ngicp_handle* h = NULL;
+  const int rc = ngicp_create(0, &h);
+  printf("%s k=%d iters=%d knn=%d hull=%d:%d%d%d%d create=%d err=%d\n", ngicp_version(), p.k_correspondences, p.max_iterations, op.submap_knn, m,
+         idx[0], idx[1], idx[2], idx[3], rc, (int)(strlen(ngicp_last_error(NULL)) > 0));
+  if (rc == NGICP_OK) ngicp_destroy(h);
+  return 0;
+}
+''')
+    exe = tmp_path / "client"
+    libdir = ROOT / "noetic-slam_b200"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{libdir}", "-lngicp_b200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    line = out.stdout.strip()
+    assert " k=20 iters=64 knn=10 hull=4:0123 " in line, line
+    import torch
+    if not torch.cuda.is_available():
+        assert f"create={B.ERR_NO_DEVICE} err=1" in line, line
